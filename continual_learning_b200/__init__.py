@@ -1,0 +1,12 @@
+"""continual_learning_b200 — B200 (sm_100a) kernels + host glue for the U-Net continual-learning step.
+
+Public surface (mirrors the reference's Python surface for this path):
+    UNet                      drop-in for models.unet.UNet (same constructor, state_dict keys)
+    CrossEntropyDistillLoss   drop-in for nn.CrossEntropyLoss() (+ optional distillation)
+    FusedAdam                 drop-in for torch.optim.Adam
+    metrics                   drop-in for the reference `metrics` module (used half)
+    TrainStep                 the fused, CUDA-graph-able step used by bench.py
+"""
+from . import _lib  # noqa: F401
+
+__all__ = ["_lib"]

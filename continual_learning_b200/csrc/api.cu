@@ -1,0 +1,595 @@
+// api.cu — the extern "C" boundary of libclk.so (declared in include/clk.h).
+// Builds TMA tensor maps + tile geometry for the igemm kernels and forwards the HBM-bound ops.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/clk.h"
+#include "igemm.cuh"
+#include "membound.cuh"
+
+using namespace clk;
+
+namespace {
+
+thread_local char g_err[512] = "";
+int g_fprop_bn = 0;
+int g_wgrad_ksplit = 0;
+int g_wgrad_bn = 64;
+int g_num_sms_api = 148;
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_status(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return CLK_OK;
+  return fail(CLK_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+inline cudaStream_t S(clk_stream_t st) { return reinterpret_cast<cudaStream_t>(st); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int ensure_encode() {
+  if (g_encode != nullptr) return CLK_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+  if (e != cudaSuccess || fn == nullptr || q != cudaDriverEntryPointSuccess)
+    return fail(CLK_E_CUDA, "cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return CLK_OK;
+}
+
+// bf16 tensor map, SWIZZLE_128B, zero OOB fill. dims/box innermost first; strides[i] = byte stride of dim i+1.
+int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+             const uint32_t* box) {
+  int rc = ensure_encode();
+  if (rc != CLK_OK) return rc;
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides[i];
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(CLK_E_BADARG, "tensor base not 16-byte aligned");
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), d, s, b, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(CLK_E_CUDA, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=[%llu,%llu,%llu,%llu,%llu] box=[%u,%u,%u,%u,%u]",
+                static_cast<int>(r), rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0,
+                rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0);
+  return CLK_OK;
+}
+
+int pow2ceil(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// NHWC activation [N][H][W][C] as a 5-D map {C, W, H, N, 1} with box {64, tw, th, nb, 1}
+int map_nhwc(CUtensorMap* m, const void* base, int N, int H, int W, int C, int tw, int th, int nb) {
+  const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N, 1};
+  const uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2,
+                          (uint64_t)N * H * W * C * 2};
+  const uint32_t box[5] = {64, (uint32_t)tw, (uint32_t)th, (uint32_t)nb, 1};
+  return make_map(m, base, 5, dims, st, box);
+}
+// [P][C] as {C, P, 1, 1, 1} with box {64, rows, 1, 1, 1}
+int map_linear(CUtensorMap* m, const void* base, long long P, int C, int rows) {
+  const uint64_t dims[5] = {(uint64_t)C, (uint64_t)P, 1, 1, 1};
+  const uint64_t pitch = (uint64_t)P * C * 2;
+  const uint64_t st[4] = {(uint64_t)C * 2, pitch, pitch, pitch};
+  const uint32_t box[5] = {64, (uint32_t)rows, 1, 1, 1};
+  return make_map(m, base, 5, dims, st, box);
+}
+// stride-2 quadrant view of y [N][2H][2W][C]: {C, 2 (j), W, 2 (i), N*H}, box {64, 1, tw, 1, th}
+int map_quad(CUtensorMap* m, const void* base, int N, int H, int W, int C, int tw, int th) {
+  const uint64_t dims[5] = {(uint64_t)C, 2, (uint64_t)W, 2, (uint64_t)N * H};
+  const uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)2 * C * 2, (uint64_t)2 * W * C * 2,
+                          (uint64_t)4 * W * C * 2};
+  const uint32_t box[5] = {64, 1, (uint32_t)tw, 1, (uint32_t)th};
+  return make_map(m, base, 5, dims, st, box);
+}
+// rows view [N*H][W][C]: {C, W, N*H, 1, 1}, box {64, tw, th, 1, 1}
+int map_rows(CUtensorMap* m, const void* base, int N, int H, int W, int C, int tw, int th) {
+  const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, (uint64_t)N * H, 1, 1};
+  const uint64_t pitch = (uint64_t)N * H * W * C * 2;
+  const uint64_t st[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, pitch, pitch};
+  const uint32_t box[5] = {64, (uint32_t)tw, (uint32_t)th, 1, 1};
+  return make_map(m, base, 5, dims, st, box);
+}
+// packed weights [T][Nrows][K] as {K, Nrows, T}, box {64, BN, 1}
+int map_weights(CUtensorMap* m, const void* base, int T, int Nrows, int K, int BN) {
+  const uint64_t dims[3] = {(uint64_t)K, (uint64_t)Nrows, (uint64_t)T};
+  const uint64_t st[2] = {(uint64_t)K * 2, (uint64_t)Nrows * K * 2};
+  const uint32_t box[3] = {64, (uint32_t)BN, 1};
+  return make_map(m, base, 3, dims, st, box);
+}
+
+void geom_nhwc(TileGeom& g, int N, int H, int W, int pixels) {
+  memset(&g, 0, sizeof(g));
+  g.mode = ADDR_NHWC;
+  g.N = N; g.H = H; g.W = W;
+  int tw = pow2ceil(W);
+  if (tw > 16) tw = 16;
+  int th = pow2ceil(H);
+  if (th > pixels / tw) th = pixels / tw;
+  g.tw = tw; g.th = th; g.nb = pixels / (tw * th);
+  g.tiles_w = (W + g.tw - 1) / g.tw;
+  g.tiles_h = (H + g.th - 1) / g.th;
+  g.tiles_n = (N + g.nb - 1) / g.nb;
+}
+void geom_linear(TileGeom& g, long long P, int pixels) {
+  memset(&g, 0, sizeof(g));
+  g.mode = ADDR_LINEAR;
+  g.N = 1; g.H = 1; g.W = static_cast<int>(P);
+  g.tw = pixels; g.th = 1; g.nb = 1;
+  g.tiles_w = static_cast<int>((P + pixels - 1) / pixels);
+  g.tiles_h = 1; g.tiles_n = 1;
+}
+void geom_quad(TileGeom& g, int N, int H, int W, int pixels) {
+  memset(&g, 0, sizeof(g));
+  g.mode = ADDR_QUAD;
+  g.N = N; g.H = H; g.W = W;
+  int tw = pow2ceil(W);
+  if (tw > 16) tw = 16;
+  g.tw = tw; g.th = pixels / tw; g.nb = 1;
+  g.tiles_w = (W + g.tw - 1) / g.tw;
+  g.tiles_h = (N * H + g.th - 1) / g.th;
+  g.tiles_n = 1;
+}
+void taps_3x3(TileGeom& g) {
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) {
+      g.t1[r * 3 + s] = s - 1;
+      g.t2[r * 3 + s] = r - 1;
+      g.t3[r * 3 + s] = 0;
+    }
+}
+void taps_quad(TileGeom& g) {
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) {
+      g.t1[i * 2 + j] = j;
+      g.t2[i * 2 + j] = 0;
+      g.t3[i * 2 + j] = i;
+    }
+}
+int num_tiles(const TileGeom& g) { return g.tiles_w * g.tiles_h * g.tiles_n; }
+
+int pick_bn(int ncols) {
+  if (g_fprop_bn > 0 && ncols % g_fprop_bn == 0) return g_fprop_bn;
+  if (ncols % 256 == 0) return 256;
+  if (ncols % 128 == 0) return 128;
+  return 64;
+}
+int pick_ksplit(int base_ctas, int tiles_total) {
+  if (g_wgrad_ksplit > 0) return g_wgrad_ksplit < tiles_total ? g_wgrad_ksplit : tiles_total;
+  int target = 2 * g_num_sms_api;
+  int ks = (target + base_ctas - 1) / base_ctas;
+  if (ks < 1) ks = 1;
+  // keep at least 8 k-steps per CTA so the pipeline fills
+  int max_ks = tiles_total / 8;
+  if (max_ks < 1) max_ks = 1;
+  if (ks > max_ks) ks = max_ks;
+  return ks;
+}
+
+#define CHECK_RC(x)            \
+  do {                         \
+    int _rc = (x);             \
+    if (_rc != CLK_OK) return _rc; \
+  } while (0)
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int clk_version(void) { return 100; }
+const char* clk_last_error(void) { return g_err; }
+
+int clk_query_device(int dev) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) return cuda_status(e, "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(CLK_E_ARCH, "device %d is sm_%d%d; libclk is built for sm_100a only (no fallback)", dev,
+                prop.major, prop.minor);
+  g_num_sms_api = prop.multiProcessorCount;
+  set_num_sms(prop.multiProcessorCount);
+  return CLK_OK;
+}
+
+int clk_set_tuning(const char* key, int value) {
+  if (key == nullptr) return fail(CLK_E_BADARG, "null key");
+  if (strcmp(key, "fprop_bn") == 0) g_fprop_bn = value;
+  else if (strcmp(key, "wgrad_ksplit") == 0) g_wgrad_ksplit = value;
+  else if (strcmp(key, "wgrad_bn") == 0) g_wgrad_bn = (value == 128 ? 128 : 64);
+  else return fail(CLK_E_BADARG, "unknown tuning key %s", key);
+  return CLK_OK;
+}
+
+// ------------------------------------------------------------------ layout / weights
+int clk_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, int Cpad, clk_stream_t st) {
+  if (!x || !y || N <= 0 || C <= 0 || Cpad < C) return fail(CLK_E_BADARG, "nchw_f32_to_nhwc_bf16: bad args");
+  return cuda_status(nchw_f32_to_nhwc_bf16(x, y, N, C, H, W, Cpad, S(st)), "nchw_f32_to_nhwc_bf16");
+}
+int clk_nhwc_to_nchw_f32(const void* x, int x_is_f32, float* y, int N, int C, int H, int W, int ldc,
+                         clk_stream_t st) {
+  if (!x || !y || N <= 0 || C <= 0 || ldc < C) return fail(CLK_E_BADARG, "nhwc_to_nchw_f32: bad args");
+  return cuda_status(nhwc_to_nchw_f32(x, x_is_f32, y, N, C, H, W, ldc, S(st)), "nhwc_to_nchw_f32");
+}
+int clk_im2col3x3_stem(const float* x, void* a, int N, int Cin, int H, int W, clk_stream_t st) {
+  if (!x || !a || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "im2col3x3_stem: bad args");
+  if (Cin * 9 > 64) return fail(CLK_E_UNSUPPORTED_SHAPE, "im2col3x3_stem: Cin*9 must be <= 64 (Cin=%d)", Cin);
+  return cuda_status(im2col3x3_stem(x, a, N, Cin, H, W, S(st)), "im2col3x3_stem");
+}
+int clk_pack_w(const float* src, void* outAB, void* outBA, int A, int B, int T, int ldA, int ldB, int ldB2,
+               int ldA2, int rev, clk_stream_t st) {
+  if (!src || A <= 0 || B <= 0 || T <= 0 || T > 9) return fail(CLK_E_BADARG, "pack_w: bad args");
+  return cuda_status(pack_w(src, outAB, outBA, A, B, T, ldA, ldB, ldB2, ldA2, rev, S(st)), "pack_w");
+}
+int clk_unpack_wgrad(const float* D, float* grad, int A, int B, int T, int ldA, int ldB, float alpha,
+                     int accumulate, clk_stream_t st) {
+  if (!D || !grad || A <= 0 || B <= 0 || T <= 0 || T > 9) return fail(CLK_E_BADARG, "unpack_wgrad: bad args");
+  return cuda_status(unpack_wgrad(D, grad, A, B, T, ldA, ldB, alpha, accumulate, S(st)), "unpack_wgrad");
+}
+
+// ------------------------------------------------------------------ igemm: conv3x3
+int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias,
+                      void* y, double* stat_sum, double* stat_sq, int N, int H, int W, int Cout, int relu,
+                      clk_stream_t st) {
+  if (!x0 || !w || !y || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "conv3x3_fprop: bad args");
+  if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (x1 == nullptr) != (C1 == 0))
+    return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_fprop: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)",
+                C0, C1, Cout);
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  geom_nhwc(p.g, N, H, W, 128);
+  taps_3x3(p.g);
+  p.ntaps = 9;
+  p.kc0 = C0 / 64;
+  p.kc1 = C1 / 64;
+  p.n_store = Cout;
+  p.dst0 = y;
+  p.ldc0 = Cout;
+  p.bias = bias;
+  p.relu = relu;
+  p.stat_sum = stat_sum;
+  p.stat_sq = stat_sq;
+  const int BN = pick_bn(Cout);
+  CUtensorMap a0, a1, b;
+  CHECK_RC(map_nhwc(&a0, x0, N, H, W, C0, p.g.tw, p.g.th, p.g.nb));
+  if (x1) CHECK_RC(map_nhwc(&a1, x1, N, H, W, C1, p.g.tw, p.g.th, p.g.nb));
+  else a1 = a0;
+  CHECK_RC(map_weights(&b, w, 9, Cout, C0 + C1, BN));
+  return cuda_status(launch_fprop(BN, 0, a0, a1, b, p, num_tiles(p.g), Cout / BN, S(st)), "conv3x3_fprop");
+}
+
+int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C0, void* dx1, int C1, int N,
+                      int H, int W, clk_stream_t st) {
+  if (!dy || !wd || !dx0 || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "conv3x3_dgrad: bad args");
+  if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (dx1 == nullptr) != (C1 == 0))
+    return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_dgrad: channels must be multiples of 64");
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  geom_nhwc(p.g, N, H, W, 128);
+  taps_3x3(p.g);
+  p.ntaps = 9;
+  p.kc0 = Cout / 64;
+  p.kc1 = 0;
+  const int Cin = C0 + C1;
+  p.n_store = Cin;
+  p.dst0 = dx0;
+  p.ldc0 = C0;
+  p.dst1 = dx1;
+  p.ldc1 = C1;
+  p.split_c = C1 > 0 ? C0 : 0;
+  int BN = pick_bn(Cin);
+  if (C1 > 0) {
+    while (BN > 64 && (C0 % BN != 0 || C1 % BN != 0)) BN >>= 1;
+  }
+  CUtensorMap a0, b;
+  CHECK_RC(map_nhwc(&a0, dy, N, H, W, Cout, p.g.tw, p.g.th, p.g.nb));
+  CHECK_RC(map_weights(&b, wd, 9, Cin, Cout, BN));
+  return cuda_status(launch_fprop(BN, 0, a0, a0, b, p, num_tiles(p.g), Cin / BN, S(st)), "conv3x3_dgrad");
+}
+
+int clk_conv3x3_wgrad(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw,
+                      int N, int H, int W, clk_stream_t st) {
+  if (!dy || !x0 || !dw || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "conv3x3_wgrad: bad args");
+  if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (x1 == nullptr) != (C1 == 0))
+    return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_wgrad: channels must be multiples of 64");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  geom_nhwc(p.g, N, H, W, 64);
+  taps_3x3(p.g);
+  const int Cin = C0 + C1;
+  int BN = g_wgrad_bn;
+  if (Cin % BN || (C1 > 0 && C0 % BN)) BN = 64;
+  p.ntaps = 9;
+  p.G = 3;
+  p.CU = Cout;
+  p.CT = Cin;
+  p.ct_split = C1 > 0 ? C0 : Cin;
+  p.m_tiles = (Cout + 127) / 128;
+  p.n_tiles = Cin / BN;
+  p.tap_groups = 3;
+  p.tiles_total = num_tiles(p.g);
+  p.ksplit = pick_ksplit(p.m_tiles * p.n_tiles * p.tap_groups, p.tiles_total);
+  p.out = dw;
+  p.ld_u = Cout;
+  p.ld_t = Cin;
+  CUtensorMap u, t0, t1;
+  CHECK_RC(map_nhwc(&u, dy, N, H, W, Cout, p.g.tw, p.g.th, p.g.nb));
+  CHECK_RC(map_nhwc(&t0, x0, N, H, W, C0, p.g.tw, p.g.th, p.g.nb));
+  if (x1) CHECK_RC(map_nhwc(&t1, x1, N, H, W, C1, p.g.tw, p.g.th, p.g.nb));
+  else t1 = t0;
+  return cuda_status(launch_wgrad(BN, u, t0, t1, p, S(st)), "conv3x3_wgrad");
+}
+
+// ------------------------------------------------------------------ igemm: plain GEMMs
+int clk_gemm_fprop(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
+                   int out_is_f32, int relu, double* stat_sum, double* stat_sq, long long P, int Npad,
+                   clk_stream_t st) {
+  if (!a || !w || !out || P <= 0) return fail(CLK_E_BADARG, "gemm_fprop: bad args");
+  if (K % 64 || K <= 0) return fail(CLK_E_UNSUPPORTED_SHAPE, "gemm_fprop: K must be a multiple of 64 (K=%d)", K);
+  if (P > 2000000000LL) return fail(CLK_E_UNSUPPORTED_SHAPE, "gemm_fprop: P too large");
+  int BN;
+  if (out_is_f32) {
+    if (Npad != 32) return fail(CLK_E_UNSUPPORTED_SHAPE, "gemm_fprop: fp32 output needs Npad == 32");
+    BN = 32;
+  } else {
+    if (Npad % 64) return fail(CLK_E_UNSUPPORTED_SHAPE, "gemm_fprop: Npad must be a multiple of 64");
+    BN = pick_bn(Npad);
+  }
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  geom_linear(p.g, P, 128);
+  p.ntaps = 1;
+  p.kc0 = K / 64;
+  p.n_store = n_store;
+  p.dst0 = out;
+  p.ldc0 = ldo;
+  p.bias = bias;
+  p.relu = relu;
+  p.stat_sum = stat_sum;
+  p.stat_sq = stat_sq;
+  CUtensorMap a0, b;
+  CHECK_RC(map_linear(&a0, a, P, K, 128));
+  CHECK_RC(map_weights(&b, w, 1, Npad, K, BN));
+  return cuda_status(launch_fprop(BN, out_is_f32, a0, a0, b, p, num_tiles(p.g), Npad / BN, S(st)), "gemm_fprop");
+}
+
+int clk_gemm_wgrad(const void* u, int CU, const void* t, int CT, float* out, int ld_u, int ld_t, long long P,
+                   clk_stream_t st) {
+  if (!u || !t || !out || P <= 0) return fail(CLK_E_BADARG, "gemm_wgrad: bad args");
+  if (CU % 64 || CT % 64) return fail(CLK_E_UNSUPPORTED_SHAPE, "gemm_wgrad: channels must be multiples of 64");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  geom_linear(p.g, P, 64);
+  p.ntaps = 1;
+  p.G = 1;
+  p.CU = CU;
+  p.CT = CT;
+  p.ct_split = CT;
+  p.m_tiles = (CU + 127) / 128;
+  p.n_tiles = CT / 64;
+  p.tap_groups = 1;
+  p.tiles_total = num_tiles(p.g);
+  p.ksplit = pick_ksplit(p.m_tiles * p.n_tiles, p.tiles_total);
+  p.out = out;
+  p.ld_u = ld_u;
+  p.ld_t = ld_t;
+  CUtensorMap mu, mt;
+  CHECK_RC(map_linear(&mu, u, P, CU, 64));
+  CHECK_RC(map_linear(&mt, t, P, CT, 64));
+  return cuda_status(launch_wgrad(64, mu, mt, mt, p, S(st)), "gemm_wgrad");
+}
+
+// ------------------------------------------------------------------ igemm: ConvTranspose2d 2x2 s2
+int clk_convT2x2_fprop(const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int Cin,
+                       int Cout, clk_stream_t st) {
+  if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "convT2x2_fprop: bad args");
+  if (Cin % 64 || Cout % 64) return fail(CLK_E_UNSUPPORTED_SHAPE, "convT2x2_fprop: channels must be multiples of 64");
+  const long long P = static_cast<long long>(N) * H * W;
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  geom_linear(p.g, P, 128);
+  p.g.N = N; p.g.H = H; p.g.W = W;  // pixel decode for the shuffle epilogue
+  p.ntaps = 1;
+  p.kc0 = Cin / 64;
+  p.shuffle = 1;
+  p.cout_q = Cout;
+  p.n_store = 4 * Cout;
+  p.dst0 = y;
+  p.ldc0 = Cout;
+  p.bias = bias;
+  const int BN = pick_bn(Cout);
+  CUtensorMap a0, b;
+  CHECK_RC(map_linear(&a0, x, P, Cin, 128));
+  CHECK_RC(map_weights(&b, w, 1, 4 * Cout, Cin, BN));
+  return cuda_status(launch_fprop(BN, 0, a0, a0, b, p, num_tiles(p.g), 4 * Cout / BN, S(st)), "convT2x2_fprop");
+}
+
+int clk_convT2x2_dgrad(const void* dy, const void* wd, void* dx, int N, int H, int W, int Cin, int Cout,
+                       clk_stream_t st) {
+  if (!dy || !wd || !dx || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "convT2x2_dgrad: bad args");
+  if (Cin % 64 || Cout % 64) return fail(CLK_E_UNSUPPORTED_SHAPE, "convT2x2_dgrad: channels must be multiples of 64");
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  geom_quad(p.g, N, H, W, 128);
+  taps_quad(p.g);
+  p.ntaps = 4;
+  p.kc0 = Cout / 64;
+  p.n_store = Cin;
+  p.dst0 = dx;
+  p.ldc0 = Cin;
+  const int BN = pick_bn(Cin);
+  CUtensorMap a0, b;
+  CHECK_RC(map_quad(&a0, dy, N, H, W, Cout, p.g.tw, p.g.th));
+  CHECK_RC(map_weights(&b, wd, 4, Cin, Cout, BN));
+  return cuda_status(launch_fprop(BN, 0, a0, a0, b, p, num_tiles(p.g), Cin / BN, S(st)), "convT2x2_dgrad");
+}
+
+int clk_convT2x2_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                       clk_stream_t st) {
+  if (!x || !dy || !dw || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "convT2x2_wgrad: bad args");
+  if (Cin % 64 || Cout % 64) return fail(CLK_E_UNSUPPORTED_SHAPE, "convT2x2_wgrad: channels must be multiples of 64");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  geom_quad(p.g, N, H, W, 64);
+  taps_quad(p.g);
+  p.ntaps = 4;
+  p.G = 4;
+  p.CU = Cin;
+  p.CT = Cout;
+  p.ct_split = Cout;
+  p.m_tiles = (Cin + 127) / 128;
+  p.n_tiles = Cout / 64;
+  p.tap_groups = 1;
+  p.tiles_total = num_tiles(p.g);
+  p.ksplit = pick_ksplit(p.m_tiles * p.n_tiles, p.tiles_total);
+  p.out = dw;
+  p.ld_u = Cin;
+  p.ld_t = Cout;
+  CUtensorMap mu, mt;
+  CHECK_RC(map_rows(&mu, x, N, H, W, Cin, p.g.tw, p.g.th));
+  CHECK_RC(map_quad(&mt, dy, N, H, W, Cout, p.g.tw, p.g.th));
+  return cuda_status(launch_wgrad(64, mu, mt, mt, p, S(st)), "convT2x2_wgrad");
+}
+
+// ------------------------------------------------------------------ BatchNorm / pool
+#define REQ_C8(name, C) \
+  if ((C) % 8 || (C) <= 0 || (C) > 2048) return fail(CLK_E_UNSUPPORTED_SHAPE, name ": C must be a multiple of 8 in (0, 2048] (C=%d)", (C))
+
+int clk_bn_stats(const void* y, double* sum, double* sq, long long P, int C, clk_stream_t st) {
+  if (!y || !sum || !sq || P <= 0) return fail(CLK_E_BADARG, "bn_stats: bad args");
+  REQ_C8("bn_stats", C);
+  return cuda_status(bn_stats(y, sum, sq, P, C, S(st)), "bn_stats");
+}
+int clk_bn_finalize(const double* sum, const double* sq, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float* mean_out, float* invstd_out, float* scale,
+                    float* shift, int C, double count, float eps, float momentum, int training,
+                    clk_stream_t st) {
+  if (!gamma || !beta || !mean_out || !invstd_out || !scale || !shift || C <= 0)
+    return fail(CLK_E_BADARG, "bn_finalize: bad args");
+  if (training && (!sum || !sq || count <= 0)) return fail(CLK_E_BADARG, "bn_finalize: training needs sums");
+  if (!training && (!running_mean || !running_var)) return fail(CLK_E_BADARG, "bn_finalize: eval needs running stats");
+  return cuda_status(bn_finalize(sum, sq, gamma, beta, running_mean, running_var, mean_out, invstd_out, scale,
+                                 shift, C, count, eps, momentum, training, S(st)),
+                     "bn_finalize");
+}
+int clk_bn_apply(const void* y, void* z, const float* scale, const float* shift, long long P, int C,
+                 clk_stream_t st) {
+  if (!y || !z || !scale || !shift || P <= 0) return fail(CLK_E_BADARG, "bn_apply: bad args");
+  REQ_C8("bn_apply", C);
+  return cuda_status(bn_apply(y, z, scale, shift, P, C, S(st)), "bn_apply");
+}
+int clk_bn_apply_pool(const void* y, void* z, void* pooled, void* idx, const float* scale, const float* shift,
+                      int N, int H, int W, int C, clk_stream_t st) {
+  if (!y || !pooled || !idx || N <= 0) return fail(CLK_E_BADARG, "bn_apply_pool: bad args");
+  if (scale && (!z || !shift)) return fail(CLK_E_BADARG, "bn_apply_pool: scale given without z/shift");
+  if (H % 2 || W % 2) return fail(CLK_E_UNSUPPORTED_SHAPE, "bn_apply_pool: H and W must be even");
+  REQ_C8("bn_apply_pool", C);
+  return cuda_status(bn_apply_pool(y, z, pooled, idx, scale, shift, N, H, W, C, S(st)), "bn_apply_pool");
+}
+int clk_maxpool_bwd_add(const void* dpooled, const void* idx, const void* skip, void* din, int N, int H, int W,
+                        int C, clk_stream_t st) {
+  if (!dpooled || !idx || !din || N <= 0) return fail(CLK_E_BADARG, "maxpool_bwd_add: bad args");
+  if (H % 2 || W % 2) return fail(CLK_E_UNSUPPORTED_SHAPE, "maxpool_bwd_add: H and W must be even");
+  REQ_C8("maxpool_bwd_add", C);
+  return cuda_status(maxpool_bwd_add(dpooled, idx, skip, din, N, H, W, C, S(st)), "maxpool_bwd_add");
+}
+int clk_bn_bwd_reduce(const void* dz, const void* y, double* s1, double* s2, long long P, int C,
+                      clk_stream_t st) {
+  if (!dz || !y || !s1 || !s2 || P <= 0) return fail(CLK_E_BADARG, "bn_bwd_reduce: bad args");
+  REQ_C8("bn_bwd_reduce", C);
+  return cuda_status(bn_bwd_reduce(dz, y, s1, s2, P, C, S(st)), "bn_bwd_reduce");
+}
+int clk_bn_bwd_finalize(const double* s1, const double* s2, const float* gamma, const float* mean,
+                        const float* invstd, float* dgamma, float* dbeta, float* kA, float* kB, float* kC, int C,
+                        double count, int training, int accumulate, clk_stream_t st) {
+  if (!s1 || !s2 || !gamma || !mean || !invstd || !dgamma || !dbeta || !kA || !kB || !kC || C <= 0 || count <= 0)
+    return fail(CLK_E_BADARG, "bn_bwd_finalize: bad args");
+  return cuda_status(bn_bwd_finalize(s1, s2, gamma, mean, invstd, dgamma, dbeta, kA, kB, kC, C, count, training,
+                                     accumulate, S(st)),
+                     "bn_bwd_finalize");
+}
+int clk_bn_relu_bwd_apply(const void* dz, const void* y, void* dpre, const float* kA, const float* kB,
+                          const float* kC, double* dbias, long long P, int C, clk_stream_t st) {
+  if (!dz || !y || !dpre || !kA || !kB || !kC || !dbias || P <= 0) return fail(CLK_E_BADARG, "bn_relu_bwd_apply: bad args");
+  REQ_C8("bn_relu_bwd_apply", C);
+  return cuda_status(bn_relu_bwd_apply(dz, y, dpre, kA, kB, kC, dbias, P, C, S(st)), "bn_relu_bwd_apply");
+}
+int clk_channel_sum(const void* g, double* out, long long P, int C, clk_stream_t st) {
+  if (!g || !out || P <= 0) return fail(CLK_E_BADARG, "channel_sum: bad args");
+  REQ_C8("channel_sum", C);
+  return cuda_status(channel_sum(g, out, P, C, S(st)), "channel_sum");
+}
+int clk_f64_to_f32(const double* src, float* dst, int n, int ld_group, int groups, float alpha, int accumulate,
+                   clk_stream_t st) {
+  if (!src || !dst || n <= 0 || groups <= 0) return fail(CLK_E_BADARG, "f64_to_f32: bad args");
+  return cuda_status(f64_to_f32(src, dst, n, ld_group, groups, alpha, accumulate, S(st)), "f64_to_f32");
+}
+
+// ------------------------------------------------------------------ loss / metrics / optimiser
+int clk_ce_kd_loss(const float* logits, const float* old_logits, const int64_t* labels, long long P, int C,
+                   int Cold, float T, float lambda, float gscale, void* dlogits, int ldd, double* loss_acc,
+                   int* err_flag, clk_stream_t st) {
+  if (!logits || !labels || !dlogits || !loss_acc || P <= 0 || C <= 0) return fail(CLK_E_BADARG, "ce_kd_loss: bad args");
+  if (ldd % 8 || ldd < C) return fail(CLK_E_UNSUPPORTED_SHAPE, "ce_kd_loss: ldd must be a multiple of 8 and >= C");
+  if (old_logits && (Cold <= 0 || Cold > C || T <= 0.f)) return fail(CLK_E_BADARG, "ce_kd_loss: bad distillation args");
+  return cuda_status(ce_kd_loss(logits, old_logits, reinterpret_cast<const long long*>(labels), P, C, Cold, T,
+                                lambda, gscale, dlogits, ldd, loss_acc, err_flag, S(st)),
+                     "ce_kd_loss");
+}
+int clk_confusion_matrix(const int64_t* target, const int64_t* pred, long long n, int nc, int64_t* conf,
+                         int* err_flag, clk_stream_t st) {
+  if (!conf || nc <= 0 || n < 0) return fail(CLK_E_BADARG, "confusion_matrix: bad args");
+  if (nc > 36) return fail(CLK_E_UNSUPPORTED_SHAPE, "confusion_matrix: nc must be <= 36 (nc=%d)", nc);
+  if (n == 0) return CLK_OK;
+  if (!target || !pred) return fail(CLK_E_BADARG, "confusion_matrix: null input");
+  if ((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(pred)) & 15)
+    return fail(CLK_E_BADARG, "confusion_matrix: inputs must be 16-byte aligned");
+  return cuda_status(confusion_matrix(reinterpret_cast<const long long*>(target),
+                                      reinterpret_cast<const long long*>(pred), n, nc,
+                                      reinterpret_cast<long long*>(conf), err_flag, S(st)),
+                     "confusion_matrix");
+}
+int clk_argmax_confusion(const float* logits, const int64_t* labels, long long P, int C, int nc, int64_t* pred_out,
+                         int64_t* conf, int64_t* correct, clk_stream_t st) {
+  if (!logits || !labels || P <= 0 || C <= 0) return fail(CLK_E_BADARG, "argmax_confusion: bad args");
+  if (conf && (nc < C || nc > 36)) return fail(CLK_E_BADARG, "argmax_confusion: need C <= nc <= 36 (a prediction >= nc has no bin)");
+  if (C > 64) return fail(CLK_E_UNSUPPORTED_SHAPE, "argmax_confusion: C must be <= 64");
+  return cuda_status(argmax_confusion(logits, reinterpret_cast<const long long*>(labels), P, C, conf ? nc : 1,
+                                      reinterpret_cast<long long*>(pred_out), reinterpret_cast<long long*>(conf),
+                                      reinterpret_cast<long long*>(correct), S(st)),
+                     "argmax_confusion");
+}
+int clk_adam_multi_tensor(const void* tensors, const void* blocks, int nblocks, int chunk, float lr, float b1,
+                          float b2, float eps, float bc1, float bc2_sqrt, float gscale, clk_stream_t st) {
+  if (!tensors || !blocks || nblocks < 0 || chunk <= 0 || chunk % 4) return fail(CLK_E_BADARG, "adam_multi_tensor: bad args");
+  return cuda_status(adam_multi_tensor(static_cast<const AdamTensor*>(tensors), blocks, nblocks, chunk, lr, b1, b2,
+                                       eps, bc1, bc2_sqrt, gscale, S(st)),
+                     "adam_multi_tensor");
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

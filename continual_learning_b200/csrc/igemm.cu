@@ -1,0 +1,499 @@
+// igemm.cu — tcgen05 / TMEM / TMA implicit-GEMM kernels (sm_100a only).
+//
+// Warp roles per CTA (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM
+// allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue (TMEM lane quadrant =
+// warp % 4).  Operand tiles are [rows][64 bf16] with SWIZZLE_128B, written by TMA and read by the
+// tensor core through UMMA shared-memory descriptors.  Accumulators live in TMEM (fp32).
+//
+// Replaces (reference): nn.Conv2d 3x3 / 1x1, nn.ConvTranspose2d 2x2 s2 forward and backward as
+// dispatched by models/unet.py:13,16,28,31,34,50,53,66,69,72 and autograd (trainer.py:175).
+#include "igemm.cuh"
+
+#include "clk_ptx.cuh"
+
+namespace clk {
+
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+
+// ------------------------------------------------------------------------------------------
+// tile -> TMA base coordinates (coords 1..4; coord 0 is always the channel)
+__device__ __forceinline__ void tile_base(const TileGeom& g, int tile, int& b1, int& b2, int& b3,
+                                          int& b4) {
+  if (g.mode == ADDR_LINEAR) {
+    b1 = tile * g.tw;
+    b2 = b3 = b4 = 0;
+  } else if (g.mode == ADDR_NHWC) {
+    const int tx = tile % g.tiles_w;
+    const int r = tile / g.tiles_w;
+    b1 = tx * g.tw;
+    b2 = (r % g.tiles_h) * g.th;
+    b3 = (r / g.tiles_h) * g.nb;
+    b4 = 0;
+  } else {  // ADDR_QUAD: coords {c, j, w, i, nh}
+    const int tx = tile % g.tiles_w;
+    b1 = 0;
+    b2 = tx * g.tw;
+    b3 = 0;
+    b4 = (tile / g.tiles_w) * g.th;
+  }
+}
+
+// row m of the tile -> linear pixel index of the tiled tensor (or -1 when outside)
+__device__ __forceinline__ long long tile_row_pixel(const TileGeom& g, int b1, int b2, int b3,
+                                                    int b4, int m, int& n, int& h, int& w) {
+  if (g.mode == ADDR_LINEAR) {
+    const long long pix = static_cast<long long>(b1) + m;
+    const long long P = static_cast<long long>(g.N) * g.H * g.W;
+    if (pix >= P) return -1;
+    w = static_cast<int>(pix % g.W);
+    const long long r = pix / g.W;
+    h = static_cast<int>(r % g.H);
+    n = static_cast<int>(r / g.H);
+    return pix;
+  } else if (g.mode == ADDR_NHWC) {
+    w = b1 + m % g.tw;
+    const int r = m / g.tw;
+    h = b2 + r % g.th;
+    n = b3 + r / g.th;
+    if (w >= g.W || h >= g.H || n >= g.N) return -1;
+    return (static_cast<long long>(n) * g.H + h) * g.W + w;
+  } else {
+    w = b2 + m % g.tw;
+    const int nh = b4 + m / g.tw;
+    if (w >= g.W || nh >= g.N * g.H) return -1;
+    n = nh / g.H;
+    h = nh % g.H;
+    return static_cast<long long>(nh) * g.W + w;
+  }
+}
+
+__device__ __forceinline__ uint8_t* align1024(uint8_t* raw) {
+  const uint32_t s = smem_u32(raw);
+  return raw + ((1024u - (s & 1023u)) & 1023u);
+}
+
+// ------------------------------------------------------------------------------------------
+// FPROP: D[128 pixels, BN] = sum_{tap, chunk} A_tile(tap, chunk)[128 x 64] * B(tap, chunk)[BN x 64]^T
+template <int BN, int STAGES, typename OutT>
+__global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
+    igemm_fprop_kernel(const __grid_constant__ CUtensorMap mapA0,
+                       const __grid_constant__ CUtensorMap mapA1,
+                       const __grid_constant__ CUtensorMap mapB,
+                       const __grid_constant__ FpropParams p) {
+  constexpr int A_BYTES = 128 * 128;
+  constexpr int B_BYTES = BN * 128;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+  float* s_sum = s_bias + BN;
+  float* s_sq = s_sum + BN;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * BN;
+  const int kc = p.kc0 + p.kc1;
+  const int num_kb = p.ntaps * kc;
+  int b1, b2, b3, b4;
+  tile_base(p.g, blockIdx.x, b1, b2, b3, b4);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < BN; i += kThreads) {
+    float bv = 0.f;
+    if (p.bias != nullptr) {
+      const int col = n0 + i;
+      if (p.shuffle) bv = p.bias[col % p.cout_q];
+      else if (col < p.n_store) bv = p.bias[col];
+    }
+    s_bias[i] = bv;
+    s_sum[i] = 0.f;
+    s_sq[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (elect_one()) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
+        const int tap = kb / kc;
+        const int ch = kb - tap * kc;
+        const int c1 = b1 + p.g.t1[tap], c2 = b2 + p.g.t2[tap], c3 = b3 + p.g.t3[tap];
+        if (ch < p.kc0)
+          tma_load_5d(sA + s * A_BYTES, &mapA0, &full[s], ch * 64, c1, c2, c3, b4);
+        else
+          tma_load_5d(sA + s * A_BYTES, &mapA1, &full[s], (ch - p.kc0) * 64, c1, c2, c3, b4);
+        tma_load_3d(sB + s * B_BYTES, &mapB, &full[s], ch * 64, n0, tap);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer (single thread)
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a = smem_u32(sA + s * A_BYTES);
+        const uint32_t b = smem_u32(sB + s * B_BYTES);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          umma_bf16(tmem_base, umma_smem_desc(a + k * 32, 16, 1024),
+                    umma_smem_desc(b + k * 32, 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------ epilogue: TMEM -> regs -> global
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    int pn = 0, ph_ = 0, pw = 0;
+    long long pix = tile_row_pixel(p.g, b1, b2, b3, b4, m, pn, ph_, pw);
+    const bool valid = pix >= 0;
+    OutT* dst = reinterpret_cast<OutT*>(p.dst0);
+    int ld = p.ldc0;
+    int colbase = n0;
+    if (p.shuffle) {
+      const int qd = n0 / p.cout_q;
+      colbase = n0 - qd * p.cout_q;
+      pix = (static_cast<long long>(pn) * (2 * p.g.H) + 2 * ph_ + (qd >> 1)) * (2 * p.g.W) +
+            2 * pw + (qd & 1);
+    } else if (p.split_c > 0 && n0 >= p.split_c) {
+      dst = reinterpret_cast<OutT*>(p.dst1);
+      ld = p.ldc1;
+      colbase = n0 - p.split_c;
+    }
+    OutT* drow = dst + (valid ? pix : 0) * ld + colbase;
+    const bool do_stats = p.stat_sum != nullptr;
+    float* scratch = reinterpret_cast<float*>(sA) + (warp - 2) * (32 * 33);
+
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + chunk * 32, v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(v[j]) + s_bias[chunk * 32 + j];
+        if (p.relu) x = fmaxf(x, 0.f);
+        f[j] = x;
+      }
+      if constexpr (sizeof(OutT) == 2) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+        if (valid && (n0 + chunk * 32) < p.n_store) {
+          uint4* o = reinterpret_cast<uint4*>(drow + chunk * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        if (do_stats) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            f[2 * j] = valid ? bf16lo_to_f32(pk[j]) : 0.f;
+            f[2 * j + 1] = valid ? bf16hi_to_f32(pk[j]) : 0.f;
+          }
+        }
+      } else {
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + chunk * 32 + j < p.n_store) drow[chunk * 32 + j] = f[j];
+        }
+        if (do_stats) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = valid ? f[j] : 0.f;
+        }
+      }
+      if (do_stats) {
+        // 32x32 transpose through shared memory: lane j then owns column (chunk*32 + j)
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = f[j];
+        __syncwarp();
+        float s = 0.f, sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float x = scratch[i * 33 + lane];
+          s += x;
+          sq = fmaf(x, x, sq);
+        }
+        atomicAdd(&s_sum[chunk * 32 + lane], s);
+        atomicAdd(&s_sq[chunk * 32 + lane], sq);
+      }
+    }
+    if (do_stats) {
+      named_bar_sync(1, kEpiThreads);
+      for (int i = threadIdx.x - 64; i < BN; i += kEpiThreads) {
+        if (n0 + i < p.n_store) {
+          atomicAdd(&p.stat_sum[n0 + i], static_cast<double>(s_sum[i]));
+          atomicAdd(&p.stat_sq[n0 + i], static_cast<double>(s_sq[i]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------
+// WGRAD: D[g][128 u, BN t] = sum_{pixel tiles} U_tile[64 px x 128 u]^T * T_tile(tap g)[64 px x BN t]
+constexpr int kWgStagesMax = 8;
+constexpr int kWgSlab = 64 * 128;  // [64 pixels][64 channels] bf16
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+    igemm_wgrad_kernel(const __grid_constant__ CUtensorMap mapU,
+                       const __grid_constant__ CUtensorMap mapT0,
+                       const __grid_constant__ CUtensorMap mapT1,
+                       const __grid_constant__ WgradParams p, const int stages,
+                       const uint32_t tmem_cols) {
+  constexpr int NBS = BN / 64;  // T slabs per tap
+  const int stage_bytes = (2 + p.G * NBS) * kWgSlab;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
+  uint64_t* empty = full + kWgStagesMax;
+  uint64_t* tmem_full = empty + kWgStagesMax;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  int bid = blockIdx.x;
+  const int mt = bid % p.m_tiles;
+  bid /= p.m_tiles;
+  const int nt = bid % p.n_tiles;
+  const int tg = bid / p.n_tiles;
+  const int tap0 = tg * p.G;
+  const int gcount = min(p.G, p.ntaps - tap0);
+  const int cu0 = mt * 128;
+  const int ct0 = nt * BN;
+  const int per = (p.tiles_total + p.ksplit - 1) / p.ksplit;
+  const int t_begin = blockIdx.y * per;
+  const int num_kb = min(p.tiles_total, t_begin + per) - t_begin;
+  if (num_kb <= 0) return;
+  const int u_slabs = (cu0 + 64 < p.CU) ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&mapU);
+    tma_prefetch_desc(&mapT0);
+    tma_prefetch_desc(&mapT1);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t tx_bytes = static_cast<uint32_t>(u_slabs + gcount * NBS) * kWgSlab;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], tx_bytes);
+        int b1, b2, b3, b4;
+        tile_base(p.g, t_begin + kb, b1, b2, b3, b4);
+        uint8_t* sU = smem + s * stage_bytes;
+        uint8_t* sT = sU + 2 * kWgSlab;
+        // U is never shifted; in ADDR_QUAD it is the plain [N*H][W][C] view of the low-res tensor
+        int u1 = b1, u2 = b2, u3 = b3, u4 = b4;
+        if (p.g.mode == ADDR_QUAD) {
+          u1 = b2;
+          u2 = b4;
+          u3 = 0;
+          u4 = 0;
+        }
+        for (int i = 0; i < u_slabs; ++i)
+          tma_load_5d(sU + i * kWgSlab, &mapU, &full[s], cu0 + i * 64, u1, u2, u3, u4);
+        for (int g = 0; g < gcount; ++g) {
+          const int tap = tap0 + g;
+          const int c1 = b1 + p.g.t1[tap], c2 = b2 + p.g.t2[tap], c3 = b3 + p.g.t3[tap];
+#pragma unroll
+          for (int j = 0; j < NBS; ++j) {
+            const int ct = ct0 + j * 64;
+            uint8_t* d = sT + (g * NBS + j) * kWgSlab;
+            if (ct < p.ct_split)
+              tma_load_5d(d, &mapT0, &full[s], ct, c1, c2, c3, b4);
+            else
+              tma_load_5d(d, &mapT1, &full[s], ct - p.ct_split, c1, c2, c3, b4);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (kb / stages) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t u = smem_u32(smem + s * stage_bytes);
+        const uint32_t t = u + 2 * kWgSlab;
+        for (int g = 0; g < gcount; ++g) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(tmem_base + g * BN, umma_smem_desc(u + k * 2048, kWgSlab, 1024),
+                      umma_smem_desc(t + g * NBS * kWgSlab + k * 2048, kWgSlab, 1024), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int u = cu0 + row;
+    const bool valid = u < p.CU;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    for (int g = 0; g < gcount; ++g) {
+      float* orow = p.out + (static_cast<size_t>(tap0 + g) * p.ld_u + (valid ? u : 0)) * p.ld_t + ct0;
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN + chunk * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (ct0 + chunk * 32 + j < p.CT) atomicAdd(orow + chunk * 32 + j, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+template <int BN, int STAGES>
+static constexpr int fprop_smem_bytes() {
+  return STAGES * (128 * 128 + BN * 128) + (2 * STAGES + 1) * 8 + 16 + 3 * BN * 4 + 1024;
+}
+
+template <int BN, int STAGES, typename OutT>
+static cudaError_t launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1,
+                                  const CUtensorMap& b, const FpropParams& p, int m_tiles,
+                                  int n_tiles, cudaStream_t st) {
+  constexpr int smem = fprop_smem_bytes<BN, STAGES>();
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_fprop_kernel<BN, STAGES, OutT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  igemm_fprop_kernel<BN, STAGES, OutT>
+      <<<dim3(m_tiles, n_tiles), kThreads, smem, st>>>(a0, a1, b, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fprop(int BN, int out_is_f32, const CUtensorMap& a0, const CUtensorMap& a1,
+                         const CUtensorMap& b, const FpropParams& p, int m_tiles, int n_tiles,
+                         cudaStream_t st) {
+  if (out_is_f32) {
+    if (BN == 32) return launch_fprop_t<32, 4, float>(a0, a1, b, p, m_tiles, n_tiles, st);
+    return cudaErrorInvalidValue;
+  }
+  switch (BN) {
+    case 64: return launch_fprop_t<64, 4, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
+    case 128: return launch_fprop_t<128, 3, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
+    case 256: return launch_fprop_t<256, 4, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int BN>
+static cudaError_t launch_wgrad_t(const CUtensorMap& u, const CUtensorMap& t0,
+                                  const CUtensorMap& t1, const WgradParams& p, cudaStream_t st) {
+  const int stage_bytes = (2 + p.G * (BN / 64)) * kWgSlab;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > kWgStagesMax) stages = kWgStagesMax;
+  if (stages < 2) return cudaErrorInvalidValue;
+  const int smem = stages * stage_bytes + (2 * kWgStagesMax + 1) * 8 + 16 + 1024;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(p.G * BN)) cols <<= 1;
+  if (cols > 512) return cudaErrorInvalidValue;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_kernel<BN>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  dim3 grid(p.m_tiles * p.n_tiles * p.tap_groups, p.ksplit);
+  igemm_wgrad_kernel<BN><<<grid, kThreads, smem, st>>>(u, t0, t1, p, stages, cols);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wgrad(int BN, const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
+                         const WgradParams& p, cudaStream_t st) {
+  switch (BN) {
+    case 64: return launch_wgrad_t<64>(u, t0, t1, p, st);
+    case 128: return launch_wgrad_t<128>(u, t0, t1, p, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace clk

@@ -1,0 +1,74 @@
+// igemm.cuh — parameter blocks and host launchers of the tcgen05 implicit-GEMM kernels.
+//
+// Two kernels cover every dense contraction of the U-Net step:
+//   * igemm_fprop: D[pixels, n] = sum_{tap, k} A[pixel (+) tap, k] * B[tap][n][k]
+//       A = NHWC bf16 activations (K-major via TMA, zero fill outside the image = conv padding),
+//       up to two A sources whose channels are walked back to back (skip-connection concat folded
+//       into the addressing, reference models/unet.py:83-87), B = packed bf16 weights.
+//       Used for conv3x3 forward + dgrad, ConvTranspose2d forward + dgrad, conv1x1 forward + dgrad.
+//   * igemm_wgrad: D[tap][u, t] = sum_{pixels} U[pixel, u] * T[pixel (+) tap, t]
+//       both operands MN-major straight out of NHWC memory; split-K over pixel tiles with fp32
+//       red.global accumulation.  Used for every weight gradient.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace clk {
+
+enum AddrMode : int {
+  ADDR_LINEAR = 0,  // A is [P][C]; tile = consecutive pixels; no taps
+  ADDR_NHWC = 1,    // A is [N][H][W][C]; tile = nb x th x tw pixels; taps shift (h, w); OOB -> 0
+  ADDR_QUAD = 2     // A is the stride-2 quadrant view [N*H][2][W][2][C] of a [N][2H][2W][C] tensor
+};
+
+constexpr int kMaxTaps = 9;
+
+struct TileGeom {
+  int mode;                       // AddrMode
+  int tw, th, nb;                 // tile = nb*th*tw pixels (ADDR_QUAD: th rows of the merged N*H axis, nb=1)
+  int tiles_w, tiles_h, tiles_n;  // tile grid (LINEAR: tiles_w only; QUAD: tiles_w x tiles_h)
+  int N, H, W;                    // pixel grid of the tiled tensor
+  int t1[kMaxTaps], t2[kMaxTaps], t3[kMaxTaps];  // per-tap offsets added to TMA coords 1..3
+};
+
+struct FpropParams {
+  TileGeom g;
+  int ntaps;
+  int kc0, kc1;        // 64-channel K chunks taken from A source 0 / source 1
+  // epilogue
+  int shuffle;         // ConvTranspose2d pixel shuffle: column = quadrant*cout_q + o
+  int cout_q;
+  int n_store;         // columns >= n_store are not stored (padding columns)
+  int split_c;         // columns >= split_c go to dst1 (0 = single destination)
+  void* dst0;
+  void* dst1;
+  int ldc0, ldc1;      // row pitch (elements) of dst0 / dst1
+  const float* bias;   // per output channel (per o when shuffle); may be null
+  int relu;
+  double* stat_sum;    // per-column sum / sum of squares of the stored values; may be null
+  double* stat_sq;
+};
+
+struct WgradParams {
+  TileGeom g;          // tile = 64 pixels
+  int ntaps;           // all taps of the operator
+  int G;               // taps accumulated per CTA (<= 4, G*BN <= 512)
+  int CU;              // valid channels of U (rows of D)
+  int CT;              // channels of T over both sources (columns of D)
+  int ct_split;        // channels that live in T source 0
+  int m_tiles, n_tiles, tap_groups;
+  int ksplit, tiles_total;
+  float* out;          // [ntaps][ld_u][ld_t] fp32, accumulated with red.add (caller zeroes)
+  int ld_u, ld_t;
+};
+
+// Launchers (igemm.cu). Return cudaError_t from the launch; maps are built by the caller.
+cudaError_t launch_fprop(int BN, int out_is_f32, const CUtensorMap& a0, const CUtensorMap& a1,
+                         const CUtensorMap& b, const FpropParams& p, int m_tiles, int n_tiles,
+                         cudaStream_t st);
+cudaError_t launch_wgrad(int BN, const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
+                         const WgradParams& p, cudaStream_t st);
+cudaError_t igemm_set_attributes();
+
+}  // namespace clk

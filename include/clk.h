@@ -1,0 +1,152 @@
+/* clk.h — C ABI of libclk.so: the B200 (sm_100a) kernels behind the U-Net training step.
+ *
+ * The reference (LorenzoFramba/Continual-Learning) has no FFI of its own: its "operator API" for this
+ * path is the stock PyTorch module calls made by models/unet.py and trainer.py.  Each entry point
+ * below names the reference call site (file:line under /root/reference) whose arithmetic it replaces;
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns an int status (CLK_OK or a negative CLK_E_*), never throws;
+ *     clk_last_error() returns a thread-local message for the last failure on this thread;
+ *   - all tensor arguments are caller-owned DEVICE pointers; nothing persistent is allocated;
+ *   - every launch is asynchronous on the given stream (a cudaStream_t passed as void*);
+ *   - activations are NHWC bf16 ("pixels x channels", channel counts multiples of 64 unless stated),
+ *     statistics / parameters / gradients are fp32, accumulators marked "f64" are double;
+ *   - there is no fallback: a device that is not sm_100 makes clk_query_device() fail.
+ */
+#ifndef CLK_H_
+#define CLK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLK_OK 0
+#define CLK_E_BADARG (-1)
+#define CLK_E_UNSUPPORTED_SHAPE (-2)
+#define CLK_E_WORKSPACE (-3)
+#define CLK_E_CUDA (-4)
+#define CLK_E_ARCH (-5)
+
+typedef void* clk_stream_t;
+
+/* ---- library ---- */
+int clk_version(void);
+const char* clk_last_error(void);
+/* CLK_OK iff device `dev` is compute capability 10.x; caches the SM count for grid sizing. */
+int clk_query_device(int dev);
+/* tuning knobs ("fprop_bn": force the N tile, 0 = auto; "wgrad_ksplit": force split-K, 0 = auto). */
+int clk_set_tuning(const char* key, int value);
+
+/* ---- layout (trainer.py:168 inputs.to(device); models/unet.py:74 forward input/output) ---- */
+int clk_nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, int Cpad,
+                              clk_stream_t st);
+int clk_nhwc_to_nchw_f32(const void* x, int x_is_f32, float* y, int N, int C, int H, int W, int ldc,
+                         clk_stream_t st);
+/* stem im2col for the Cin<=7 first conv (models/unet.py:50): A[N*H*W][64] bf16, k = c*9+r*3+s. */
+int clk_im2col3x3_stem(const float* x_nchw, void* a, int N, int Cin, int H, int W, clk_stream_t st);
+
+/* ---- weights: fp32 PyTorch layout <-> packed bf16 operand layout ----
+ * src fp32 [A][B][T] (Conv2d: A=Cout,B=Cin,T=kh*kw; ConvTranspose2d: A=Cin,B=Cout,T=4)
+ * outAB bf16 [T][ldA][ldB], outBA bf16 [T][ldB2][ldA2] (tap order reversed when rev!=0); either may be NULL. */
+int clk_pack_w(const float* src, void* outAB, void* outBA, int A, int B, int T, int ldA, int ldB,
+               int ldB2, int ldA2, int rev, clk_stream_t st);
+/* grad[A][B][T] (=|+=) alpha * D[T][ldA][ldB]   (D = packed fp32 weight gradient) */
+int clk_unpack_wgrad(const float* D, float* grad, int A, int B, int T, int ldA, int ldB, float alpha,
+                     int accumulate, clk_stream_t st);
+
+/* ---- tcgen05 implicit GEMMs ----
+ * conv3x3, stride 1, zero pad 1 (nn.Conv2d at models/unet.py:13,16,28,31,53,66,69) fused with
+ * bias + ReLU (models/unet.py:14,17,...) and the per-channel sum / sum-of-squares BatchNorm needs.
+ * The input may be two tensors whose channels are concatenated (torch.cat at models/unet.py:83-87,
+ * skip first): x0 has C0 channels, x1 has C1 (x1 may be NULL with C1 = 0).
+ * w: bf16 [9][Cout][C0+C1] (clk_pack_w outAB).  y: bf16 [N][H][W][Cout].  stat_*: f64[Cout] or NULL. */
+int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias,
+                      void* y, double* stat_sum, double* stat_sq, int N, int H, int W, int Cout, int relu,
+                      clk_stream_t st);
+/* dgrad of the same conv (autograd of trainer.py:175): dy bf16 [N][H][W][Cout],
+ * wd bf16 [9][C0+C1][Cout] (clk_pack_w outBA, rev=1); writes dx0 [..][C0] and dx1 [..][C1]. */
+int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C0, void* dx1, int C1,
+                      int N, int H, int W, clk_stream_t st);
+/* wgrad: dw fp32 [9][Cout][C0+C1] += sum_pixels dy (x) shifted x.  Caller zeroes dw. */
+int clk_conv3x3_wgrad(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw,
+                      int N, int H, int W, clk_stream_t st);
+/* plain GEMM out[P][.] = a[P][K] * w[Npad][K]^T (+bias, ReLU, stats): the im2col'ed stem conv
+ * (models/unet.py:50), the 1x1 head (models/unet.py:72; fp32 output, n_store = num_classes) and the
+ * head dgrad.  K % 64 == 0; Npad in {32 (f32 out), 64, 128, 256 multiples}. */
+int clk_gemm_fprop(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
+                   int out_is_f32, int relu, double* stat_sum, double* stat_sq, long long P, int Npad,
+                   clk_stream_t st);
+/* out fp32 [ld_u][ld_t] += u[P][CU]^T * t[P][CT]  (weight gradient of the GEMMs above) */
+int clk_gemm_wgrad(const void* u, int CU, const void* t, int CT, float* out, int ld_u, int ld_t,
+                   long long P, clk_stream_t st);
+/* ConvTranspose2d k=2 s=2 (models/unet.py:34): x bf16 [N][H][W][Cin], w bf16 [4*Cout][Cin]
+ * (clk_pack_w outBA, rev=0), y bf16 [N][2H][2W][Cout] written through the pixel-shuffle epilogue. */
+int clk_convT2x2_fprop(const void* x, const void* w, const float* bias, void* y, int N, int H, int W,
+                       int Cin, int Cout, clk_stream_t st);
+/* dx[N][H][W][Cin] from dy[N][2H][2W][Cout]; wd bf16 [4][Cin][Cout] (clk_pack_w outAB). */
+int clk_convT2x2_dgrad(const void* dy, const void* wd, void* dx, int N, int H, int W, int Cin, int Cout,
+                       clk_stream_t st);
+/* dw fp32 [4][Cin][Cout] += ...; caller zeroes. */
+int clk_convT2x2_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin, int Cout,
+                       clk_stream_t st);
+
+/* ---- BatchNorm2d (models/unet.py:15,18,30,33,52,55,68,71), eps/momentum as nn defaults ---- */
+int clk_bn_stats(const void* y, double* sum, double* sq, long long P, int C, clk_stream_t st);
+/* training: batch mean / biased var -> mean, invstd, scale=gamma*invstd, shift=beta-mean*scale and the
+ * running-stat EMA (unbiased var); eval (training=0): coefficients from the running stats. */
+int clk_bn_finalize(const double* sum, const double* sq, const float* gamma, const float* beta,
+                    float* running_mean, float* running_var, float* mean_out, float* invstd_out,
+                    float* scale, float* shift, int C, double count, float eps, float momentum,
+                    int training, clk_stream_t st);
+int clk_bn_apply(const void* y, void* z, const float* scale, const float* shift, long long P, int C,
+                 clk_stream_t st);
+/* BN apply fused with MaxPool2d(2,2) (models/unet.py:12,80): z and pooled + 1-byte window index.
+ * scale == NULL: pooling only (z untouched). */
+int clk_bn_apply_pool(const void* y, void* z, void* pooled, void* idx, const float* scale,
+                      const float* shift, int N, int H, int W, int C, clk_stream_t st);
+/* din = scatter(dpooled by idx) + skip (skip may be NULL): max-pool backward fused with the
+ * skip-connection gradient sum. */
+int clk_maxpool_bwd_add(const void* dpooled, const void* idx, const void* skip, void* din, int N, int H,
+                        int W, int C, clk_stream_t st);
+int clk_bn_bwd_reduce(const void* dz, const void* y, double* s1, double* s2, long long P, int C,
+                      clk_stream_t st);
+int clk_bn_bwd_finalize(const double* s1, const double* s2, const float* gamma, const float* mean,
+                        const float* invstd, float* dgamma, float* dbeta, float* kA, float* kB, float* kC,
+                        int C, double count, int training, int accumulate, clk_stream_t st);
+/* dpre = relu'(y) * (kA*dz + kB*y + kC); dbias f64[C] += sum dpre */
+int clk_bn_relu_bwd_apply(const void* dz, const void* y, void* dpre, const float* kA, const float* kB,
+                          const float* kC, double* dbias, long long P, int C, clk_stream_t st);
+int clk_channel_sum(const void* g, double* out, long long P, int C, clk_stream_t st);
+int clk_f64_to_f32(const double* src, float* dst, int n, int ld_group, int groups, float alpha,
+                   int accumulate, clk_stream_t st);
+
+/* ---- loss: nn.CrossEntropyLoss (trainer.py:113,174) fused with the temperature-KL distillation
+ * term of the continual step (not in the reference) and with its own backward ----
+ * logits fp32 [P][C]; old_logits fp32 [P][Cold] or NULL; labels int64 [P];
+ * dlogits bf16 [P][ldd] (columns >= C zero); loss_acc f64[2] += {sum CE, sum KD}. */
+int clk_ce_kd_loss(const float* logits, const float* old_logits, const int64_t* labels, long long P, int C,
+                   int Cold, float T, float lambda, float gscale, void* dlogits, int ldd, double* loss_acc,
+                   int* err_flag, clk_stream_t st);
+
+/* ---- metrics (metrics.py:32-38,55-63; trainer.py:183-184,279-280) ---- */
+/* conf int64 [nc*nc] += bincount(nc*t+p) over 0<=t<nc; *err_flag=1 if a kept target has p outside [0,nc). */
+int clk_confusion_matrix(const int64_t* target, const int64_t* pred, long long n, int nc, int64_t* conf,
+                         int* err_flag, clk_stream_t st);
+/* argmax over fp32 logits [P][C] + confusion + correct count in one pass; any output may be NULL. */
+int clk_argmax_confusion(const float* logits, const int64_t* labels, long long P, int C, int nc,
+                         int64_t* pred_out, int64_t* conf, int64_t* correct, clk_stream_t st);
+
+/* ---- optimiser: torch.optim.Adam step (trainer.py:108-110,176) over a table of tensors ----
+ * tensors: device array of {float* p; const float* g; float* m; float* v; int64 numel};
+ * blocks: device array of int2 {tensor index, chunk index}; bc1 = 1-b1^t, bc2_sqrt = sqrt(1-b2^t). */
+int clk_adam_multi_tensor(const void* tensors, const void* blocks, int nblocks, int chunk, float lr,
+                          float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale,
+                          clk_stream_t st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLK_H_ */
