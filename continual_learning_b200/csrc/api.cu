@@ -584,10 +584,11 @@ int clk_argmax_confusion(const float* logits, const int64_t* labels, long long P
                      "argmax_confusion");
 }
 int clk_adam_multi_tensor(const void* tensors, const void* blocks, int nblocks, int chunk, float lr, float b1,
-                          float b2, float eps, float bc1, float bc2_sqrt, float gscale, clk_stream_t st) {
+                          float b2, float eps, float bc1, float bc2_sqrt, float gscale, const float* hyper_dev,
+                          clk_stream_t st) {
   if (!tensors || !blocks || nblocks < 0 || chunk <= 0 || chunk % 4) return fail(CLK_E_BADARG, "adam_multi_tensor: bad args");
   return cuda_status(adam_multi_tensor(static_cast<const AdamTensor*>(tensors), blocks, nblocks, chunk, lr, b1, b2,
-                                       eps, bc1, bc2_sqrt, gscale, S(st)),
+                                       eps, bc1, bc2_sqrt, gscale, hyper_dev, S(st)),
                      "adam_multi_tensor");
 }
 

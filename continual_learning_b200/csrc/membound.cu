@@ -892,7 +892,13 @@ cudaError_t argmax_confusion(const float* logits, const long long* labels, long 
 //   m = b1*m + (1-b1)*g ; v = b2*v + (1-b2)*g*g ; p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
 __global__ void adam_kernel(const AdamTensor* __restrict__ tensors, const int2* __restrict__ blocks,
                             int chunk, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-                            float gscale) {
+                            float gscale, const float* __restrict__ hyper) {
+  if (hyper != nullptr) {  // {lr, bc1, bc2_sqrt, gscale} in device memory (CUDA-graph replay)
+    lr = hyper[0];
+    bc1 = hyper[1];
+    bc2_sqrt = hyper[2];
+    gscale = hyper[3];
+  }
   const int2 blk = blocks[blockIdx.x];
   const AdamTensor t = tensors[blk.x];
   const long long begin = static_cast<long long>(blk.y) * chunk;
@@ -939,10 +945,10 @@ __global__ void adam_kernel(const AdamTensor* __restrict__ tensors, const int2* 
 }
 cudaError_t adam_multi_tensor(const AdamTensor* tensors, const void* blocks, int nblocks, int chunk,
                               float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-                              float gscale, cudaStream_t st) {
+                              float gscale, const float* hyper, cudaStream_t st) {
   if (nblocks <= 0) return cudaSuccess;
   adam_kernel<<<nblocks, 256, 0, st>>>(tensors, static_cast<const int2*>(blocks), chunk, lr, b1, b2, eps,
-                                       bc1, bc2_sqrt, gscale);
+                                       bc1, bc2_sqrt, gscale, hyper);
   return cudaGetLastError();
 }
 

@@ -55,6 +55,6 @@ cudaError_t argmax_confusion(const float* logits, const long long* labels, long 
                              long long* pred_out, long long* conf, long long* correct, cudaStream_t st);
 cudaError_t adam_multi_tensor(const AdamTensor* tensors, const void* blocks, int nblocks, int chunk,
                               float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
-                              float gscale, cudaStream_t st);
+                              float gscale, const float* hyper, cudaStream_t st);
 
 }  // namespace clk

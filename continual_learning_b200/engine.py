@@ -1,0 +1,267 @@
+"""UNetEngine — launch schedule of the U-Net forward / backward over libclk kernels.
+
+Reference path: models/unet.py:74-92 (forward) and the autograd graph behind trainer.py:175.
+Data layout in HBM: every activation is NHWC bf16; per conv->ReLU->BN unit the engine keeps
+`y = relu(conv(x)+b)` and `z = BN(y)` (plus the 2x2-pooled `z` and its window index for the encoder
+outputs).  Skip-connection concats (models/unet.py:83-87) are never materialised: the conv kernels
+walk the channels of the two source tensors back to back.  fp32 master parameters stay in the
+nn.Module; bf16 packed operand copies are refreshed whenever a parameter version changes.
+"""
+import torch
+
+from . import _lib, ops
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+f64 = torch.float64
+
+
+class _Unit:
+    """one Conv3x3(+bias) -> ReLU -> BatchNorm2d triple (models/unet.py:13-15)."""
+
+    def __init__(self, conv, bn, c0, c1, cout, stem=False):
+        self.conv, self.bn, self.c0, self.c1, self.cout, self.stem = conv, bn, c0, c1, cout, stem
+        self.x0 = self.x1 = self.y = self.z = self.pooled = self.idx = None
+
+
+class UNetEngine:
+    def __init__(self, module):
+        self.m = module
+        m = module
+        c = m.conv_dim
+        if c % 64 != 0:
+            raise ValueError("the sm_100a kernels need conv_dim to be a multiple of 64")
+        if m.in_dim * 9 > 64:
+            raise ValueError("the stem kernel needs in_dim*9 <= 64")
+        if m.num_classes > 32:
+            raise ValueError("the head kernel needs num_classes <= 32")
+        e1 = m.enc1
+        self.units = [_Unit(e1[0], e1[2], 64, 0, c, stem=True), _Unit(e1[3], e1[5], c, 0, c)]
+        for blk, ci, co in ((m.enc2, c, 2 * c), (m.enc3, 2 * c, 4 * c), (m.enc4, 4 * c, 8 * c)):
+            b = blk.block
+            self.units += [_Unit(b[1], b[3], ci, 0, co), _Unit(b[4], b[6], co, 0, co)]
+        self.convT = []
+        first = True
+        for blk, ci, cm, co in ((m.dec1, 8 * c, 16 * c, 8 * c), (m.dec2, 16 * c, 8 * c, 4 * c),
+                                (m.dec3, 8 * c, 4 * c, 2 * c), (m.dec4, 4 * c, 2 * c, c)):
+            b = blk.block
+            c0, c1 = (ci, 0) if first else (ci // 2, ci // 2)
+            first = False
+            self.units += [_Unit(b[0], b[2], c0, c1, cm), _Unit(b[3], b[5], cm, 0, cm)]
+            self.convT.append((b[6], cm, co))
+        self.units += [_Unit(m.last[0], m.last[2], c, c, c), _Unit(m.last[3], m.last[5], c, 0, c)]
+        self.head = m.last[6]
+        self._dev = None
+        self._wver = None
+        self.training_fwd = True
+        self.logits = None
+
+    # ------------------------------------------------------------------ persistent buffers
+    def _setup(self, dev):
+        if self._dev == dev:
+            return
+        self._dev = dev
+        self.params = list(self.m.parameters())
+        c_dim = self.m.conv_dim
+        n = sum(p.numel() for p in self.params)
+        self.G = torch.zeros(n, device=dev, dtype=f32)  # flat .grad storage, PyTorch layouts
+        self.gview = {}
+        off = 0
+        for p in self.params:
+            self.gview[p] = self.G[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        # packed fp32 weight-gradient accumulators + packed bf16 operand copies
+        sizes = []
+        for u in self.units:
+            sizes.append(64 * 64 if u.stem else 9 * u.cout * (u.c0 + u.c1))
+        for (_, cm, co) in self.convT:
+            sizes.append(4 * cm * co)
+        sizes.append(64 * c_dim)
+        self.Gp = torch.zeros(sum(sizes), device=dev, dtype=f32)
+        views, off = [], 0
+        for s in sizes:
+            views.append(self.Gp[off:off + s])
+            off += s
+        nu = len(self.units)
+        for i, u in enumerate(self.units):
+            u.gp = views[i].view(64, 64) if u.stem else views[i].view(9, u.cout, u.c0 + u.c1)
+            if u.stem:
+                u.wf = torch.zeros((u.cout, 64), device=dev, dtype=bf16)
+                u.wd = None
+            else:
+                u.wf = torch.empty((9, u.cout, u.c0 + u.c1), device=dev, dtype=bf16)
+                u.wd = torch.empty((9, u.c0 + u.c1, u.cout), device=dev, dtype=bf16)
+        self.tgp, self.twf, self.twd = [], [], []
+        for j, (_, cm, co) in enumerate(self.convT):
+            self.tgp.append(views[nu + j].view(4, cm, co))
+            self.twf.append(torch.empty((4 * co, cm), device=dev, dtype=bf16))
+            self.twd.append(torch.empty((4, cm, co), device=dev, dtype=bf16))
+        self.hgp = views[-1].view(64, c_dim)
+        self.hwf = torch.zeros((32, self.m.conv_dim), device=dev, dtype=bf16)
+        self.hwd = torch.zeros((self.m.conv_dim, 64), device=dev, dtype=bf16)
+        # fp64 per-channel accumulators: forward (sum, sq) and backward (s1, s2, dbias) per unit,
+        # dbias per convT, dbias of the head
+        fw = sum(2 * u.cout for u in self.units)
+        bw = sum(3 * u.cout for u in self.units) + sum(co for (_, _, co) in self.convT) + 64
+        self.acc_f = torch.zeros(fw, device=dev, dtype=f64)
+        self.acc_b = torch.zeros(bw, device=dev, dtype=f64)
+        of, ob = 0, 0
+        for u in self.units:
+            u.s_sum, u.s_sq = self.acc_f[of:of + u.cout], self.acc_f[of + u.cout:of + 2 * u.cout]
+            of += 2 * u.cout
+            u.s1, u.s2, u.dbias = (self.acc_b[ob + k * u.cout:ob + (k + 1) * u.cout] for k in range(3))
+            ob += 3 * u.cout
+            # fp32 per-channel vectors: mean, invstd, scale, shift, kA, kB, kC
+            u.vec = torch.empty((7, u.cout), device=dev, dtype=f32)
+        self.tdbias = []
+        for (_, _, co) in self.convT:
+            self.tdbias.append(self.acc_b[ob:ob + co])
+            ob += co
+        self.hdbias = self.acc_b[ob:ob + 64]
+        self._wver = None
+
+    def _pack_weights(self):
+        ver = tuple(p._version for p in self.params) + tuple(p.data_ptr() for p in self.params[:2])
+        if ver == self._wver:
+            return
+        for u in self.units:
+            if u.stem:
+                ops.pack_stem(u.conv.weight.detach(), u.wf)
+            else:
+                ops.pack_conv3x3(u.conv.weight.detach(), u.wf, u.wd)
+        for j, (mod, _, _) in enumerate(self.convT):
+            ops.pack_convT(mod.weight.detach(), self.twf[j], self.twd[j])
+        ops.pack_head(self.head.weight.detach(), self.hwf, self.hwd)
+        self._wver = ver
+
+    # ------------------------------------------------------------------ forward
+    def _unit_fwd(self, u, x0, x1, training, pool=False):
+        n, h, w = x0.shape[0], x0.shape[1], x0.shape[2]
+        u.x0, u.x1 = x0, x1
+        stats = (u.s_sum, u.s_sq) if training else None
+        bias = u.conv.bias.detach()
+        if u.stem:
+            u.y = ops.gemm_fprop(x0, u.wf, bias, u.cout, relu=True, stats=stats)
+        else:
+            u.y = ops.conv3x3_fprop(x0, x1, u.wf, bias, relu=True, stats=stats)
+        bn = u.bn
+        mean, invstd, scale, shift = u.vec[0], u.vec[1], u.vec[2], u.vec[3]
+        ops.bn_finalize(u.s_sum, u.s_sq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, mean,
+                        invstd, scale, shift, n * h * w, eps=bn.eps,
+                        momentum=0.1 if bn.momentum is None else bn.momentum, training=training)
+        if pool:
+            u.z, u.pooled, u.idx = ops.bn_apply_pool(u.y, scale, shift)
+        else:
+            u.z = ops.bn_apply(u.y, scale, shift)
+            u.pooled = u.idx = None
+        return u.z
+
+    def forward(self, x, training=True):
+        """x: fp32 NCHW CUDA tensor. Returns fp32 logits [N, H, W, num_classes] (NHWC memory)."""
+        if not x.is_cuda:
+            raise RuntimeError("continual_learning_b200.UNet runs on CUDA (sm_100a) only: there is no CPU fallback")
+        _lib.ensure_device(x.device.index)
+        n, cin, h, w = x.shape
+        if h % 16 or w % 16:
+            raise ValueError("input H and W must be multiples of 16 (four 2x2 pools, models/unet.py:76-80)")
+        if cin != self.m.in_dim:
+            raise ValueError(f"expected {self.m.in_dim} input channels, got {cin}")
+        self._setup(x.device)
+        self._pack_weights()
+        self.training_fwd = training
+        if training:
+            self.acc_f.zero_()
+        U = self.units
+        a = ops.im2col_stem(x.float())
+        z = self._unit_fwd(U[0], a, None, training)
+        self._unit_fwd(U[1], z, None, training, pool=True)
+        for k in (2, 4, 6):
+            z = self._unit_fwd(U[k], U[k - 1].pooled, None, training)
+            self._unit_fwd(U[k + 1], z, None, training, pool=True)
+        skips = [U[7], U[5], U[3], U[1]]
+        up = None
+        self.tin = []
+        for j in range(4):
+            k = 8 + 2 * j
+            if j == 0:
+                z = self._unit_fwd(U[k], U[7].pooled, None, training)
+            else:
+                z = self._unit_fwd(U[k], skips[j - 1].z, up, training)
+            z = self._unit_fwd(U[k + 1], z, None, training)
+            self.tin.append(z)
+            up = ops.convT_fprop(z, self.twf[j], self.convT[j][0].bias.detach())
+        z = self._unit_fwd(U[16], U[1].z, up, training)
+        z = self._unit_fwd(U[17], z, None, training)
+        self.logits = ops.gemm_fprop(z, self.hwf, self.head.bias.detach(), self.m.num_classes, out_f32=True)
+        if training:
+            bufs = [u.bn.num_batches_tracked for u in U if u.bn.num_batches_tracked is not None]
+            if bufs:
+                torch._foreach_add_(bufs, 1)
+        return self.logits
+
+    # ------------------------------------------------------------------ backward
+    def _unit_bwd(self, u, dz, need_dx=True):
+        n, h, w = dz.shape[0], dz.shape[1], dz.shape[2]
+        bn = u.bn
+        mean, invstd, ka, kb, kc = u.vec[0], u.vec[1], u.vec[4], u.vec[5], u.vec[6]
+        ops.bn_bwd_reduce(dz, u.y, u.s1, u.s2)
+        ops.bn_bwd_finalize(u.s1, u.s2, bn.weight.detach(), mean, invstd, self.gview[bn.weight], self.gview[bn.bias],
+                            ka, kb, kc, n * h * w, training=self.training_fwd)
+        dpre = ops.bn_relu_bwd_apply(dz, u.y, ka, kb, kc, u.dbias)
+        ops.f64_to_f32(u.dbias, self.gview[u.conv.bias])
+        if u.stem:
+            ops.gemm_wgrad(dpre, u.x0, out=u.gp)
+            ops.unpack_wgrad(u.gp, self.gview[u.conv.weight], u.cout, self.m.in_dim * 9, 1, 64, 64)
+            return None, None
+        ops.conv3x3_wgrad(dpre, u.x0, u.x1, out=u.gp)
+        ops.unpack_wgrad(u.gp, self.gview[u.conv.weight], u.cout, u.c0 + u.c1, 9, u.cout, u.c0 + u.c1)
+        if not need_dx:
+            return None, None
+        return ops.conv3x3_dgrad(dpre, u.wd, u.c0, u.c1)
+
+    def _convT_bwd(self, j, dy):
+        mod, cm, co = self.convT[j]
+        ops.convT_wgrad(self.tin[j], dy, out=self.tgp[j])
+        ops.unpack_wgrad(self.tgp[j], self.gview[mod.weight], cm, co, 4, cm, co)
+        ops.channel_sum(dy, self.tdbias[j])
+        ops.f64_to_f32(self.tdbias[j], self.gview[mod.bias])
+        return ops.convT_dgrad(dy, self.twd[j])
+
+    def backward(self, dlogits):
+        """dlogits: bf16 [N, H, W, 64] (columns >= num_classes zero). Fills the flat gradient buffer and
+        returns the per-parameter gradient views (PyTorch layouts) in `module.parameters()` order."""
+        U = self.units
+        nc = self.m.num_classes
+        self.acc_b.zero_()
+        self.Gp.zero_()
+        # 1x1 head (models/unet.py:72)
+        ops.gemm_wgrad(dlogits, U[17].z, out=self.hgp)
+        ops.unpack_wgrad(self.hgp, self.gview[self.head.weight], nc, self.m.conv_dim, 1, 64, self.m.conv_dim)
+        ops.channel_sum(dlogits, self.hdbias)
+        ops.f64_to_f32(self.hdbias, self.gview[self.head.bias], n=nc)
+        dz = ops.gemm_fprop(dlogits, self.hwd, None, self.m.conv_dim)
+        dz, _ = self._unit_bwd(U[17], dz)
+        skip_grads = []
+        dskip, dup = self._unit_bwd(U[16], dz)
+        skip_grads.append(dskip)  # for enc1
+        for j in (3, 2, 1, 0):
+            k = 8 + 2 * j
+            dz = self._convT_bwd(j, dup)
+            dz, _ = self._unit_bwd(U[k + 1], dz)
+            dskip, dup = self._unit_bwd(U[k], dz)
+            if j > 0:
+                skip_grads.append(dskip)  # enc2, enc3, enc4 in that order
+            else:
+                dpool = dskip  # gradient of the centre pool output
+        # encoder, deepest first: enc4 (U[7]) .. enc1 (U[1])
+        for lvl, k in ((3, 7), (2, 5), (1, 3), (0, 1)):
+            dz = ops.maxpool_bwd_add(dpool, U[k].idx, skip_grads[lvl])
+            dz, _ = self._unit_bwd(U[k], dz)
+            dpool, _ = self._unit_bwd(U[k - 1], dz, need_dx=(k > 1))
+        return [self.gview[p] for p in self.params]
+
+    def release(self):
+        """drop the saved activations (after backward, or after an eval forward)."""
+        for u in self.units:
+            u.x0 = u.x1 = u.y = u.z = u.pooled = u.idx = None
+        self.tin = []

@@ -40,7 +40,9 @@ class FusedAdam(torch.optim.Optimizer):
         return t, b, len(blocks)
 
     @torch.no_grad()
-    def step(self, closure=None, grad_scale=1.0):
+    def step(self, closure=None, grad_scale=1.0, hyper_dev=None):
+        """hyper_dev: optional device float[4] {lr, bc1, bc2_sqrt, gscale} (see `hyper_values`) read by the
+        kernel instead of the host scalars — lets a captured CUDA graph be replayed."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -69,5 +71,11 @@ class FusedAdam(torch.optim.Optimizer):
             bc2_sqrt = math.sqrt(1.0 - b2 ** step)
             t, b, nblocks = self._table(gi, plist)
             _lib.call("clk_adam_multi_tensor", t, b, nblocks, _CHUNK, float(group["lr"]), b1, b2,
-                      float(group["eps"]), bc1, bc2_sqrt, float(grad_scale))
+                      float(group["eps"]), bc1, bc2_sqrt, float(grad_scale), hyper_dev)
         return loss
+
+    def hyper_values(self, step, grad_scale=1.0, group=0):
+        """[lr, 1-b1^t, sqrt(1-b2^t), grad_scale] for optimiser step number `step` (1-based)."""
+        g = self.param_groups[group]
+        b1, b2 = g["betas"]
+        return [float(g["lr"]), 1.0 - b1 ** step, math.sqrt(1.0 - b2 ** step), float(grad_scale)]

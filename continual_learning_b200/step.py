@@ -1,0 +1,142 @@
+"""TrainStep — the whole training step of trainer.py:168-176 as one call (optionally one CUDA graph):
+
+    inputs/labels H2D -> [frozen old-model forward] -> U-Net forward -> fused CE(+KD) loss fwd+bwd
+    -> U-Net backward -> [bucketed NCCL all-reduce of the gradients] -> Adam
+
+This is the public fast path (`bench.py` e2e goes through `TrainStep.step_host`).  The drop-in
+nn.Module path (UNet + CrossEntropyDistillLoss + FusedAdam driven by the reference Trainer) launches
+exactly the same kernels through autograd.
+"""
+import torch
+
+from . import ops
+from .optim import FusedAdam
+
+
+class TrainStep:
+    def __init__(self, model, optimizer, old_model=None, T=2.0, lam=1.0, use_graph=True, comm=None):
+        if not isinstance(optimizer, FusedAdam):
+            raise TypeError("TrainStep needs continual_learning_b200.FusedAdam")
+        self.model, self.opt, self.old = model, optimizer, old_model
+        self.T, self.lam = float(T), float(lam)
+        self.use_graph = use_graph
+        self.comm = comm  # parallel.GradAllReduce or None
+        self.graph = None
+        self.shape = None
+        self.step_count = 0
+        self._opt_ready = False
+
+    # ------------------------------------------------------------------ one eager step on device tensors
+    def _body(self, x, y):
+        eng = self.model.engine
+        old_logits = None
+        if self.old is not None:
+            oeng = self.old.engine
+            old_logits = oeng.forward(x, training=False)
+            oeng.release()
+        logits = eng.forward(x, training=self.model.training)
+        self.loss_acc.zero_()
+        ops.ce_kd_loss(logits, y, old_logits, T=self.T, lam=self.lam, dlogits=self.dlogits, loss_acc=self.loss_acc,
+                       err_flag=self.err_flag)
+        views = eng.backward(self.dlogits)
+        eng.release()
+        if not self._opt_ready:
+            for p, v in zip(eng.params, views):
+                p.grad = v
+            self._opt_ready = True
+        gscale = 1.0
+        if self.comm is not None:
+            self.comm.all_reduce(eng.G)
+            gscale = 1.0 / self.comm.world_size
+        self.opt.step(grad_scale=gscale, hyper_dev=self.hyper)
+
+    def _alloc(self, x, y):
+        dev = x.device
+        n, _, h, w = x.shape
+        self.shape = (tuple(x.shape), tuple(y.shape))
+        self.x_static = torch.empty_like(x)
+        self.y_static = torch.empty_like(y)
+        self.dlogits = torch.zeros((n, h, w, 64), device=dev, dtype=torch.bfloat16)
+        self.loss_acc = torch.zeros(2, device=dev, dtype=torch.float64)
+        self.err_flag = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.hyper = torch.zeros(4, device=dev, dtype=torch.float32)
+        self.hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+        self.npix = n * h * w
+        self.graph = None
+        self._opt_ready = False
+
+    def _set_hyper(self):
+        gs = 1.0 if self.comm is None else 1.0 / self.comm.world_size
+        vals = self.opt.hyper_values(self.step_count + 1, grad_scale=gs)
+        for i, v in enumerate(vals):
+            self.hyper_host[i] = v
+        self.hyper.copy_(self.hyper_host, non_blocking=True)
+
+    def step(self, x, y):
+        """x fp32 [B,3,H,W], y int64 [B,H,W], both on the device. Returns the loss as a 0-dim fp64 device tensor."""
+        if self.shape != (tuple(x.shape), tuple(y.shape)):
+            self._alloc(x, y)
+        self._set_hyper()
+        if not self.use_graph:
+            self._body(x, y)
+        else:
+            self.x_static.copy_(x, non_blocking=True)
+            self.y_static.copy_(y, non_blocking=True)
+            if self.graph is None:
+                # warm-up eagerly on a side stream (allocator + lazy initialisation), then capture
+                state = self._snapshot()
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._body(self.x_static, self.y_static)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                self._restore(state)
+                self.model.engine._wver = None
+                if self.old is not None:
+                    self.old.engine._wver = None
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._body(self.x_static, self.y_static)
+                self.graph = g
+                self._restore(state)
+            self.graph.replay()
+        self.step_count += 1
+        for p in self.model.engine.params:
+            st = self.opt.state[p]
+            st["step"] = torch.tensor(float(self.step_count))
+        loss = self.loss_acc[0] / self.npix
+        if self.old is not None:
+            loss = loss + (self.lam * self.T * self.T / self.npix) * self.loss_acc[1]
+        return loss
+
+    def step_host(self, x_pinned, y_pinned):
+        """end-to-end step from pinned HOST tensors: H2D of the inputs, the step, D2H of the loss (float)."""
+        dev = next(self.model.parameters()).device
+        x = x_pinned.to(dev, non_blocking=True)
+        y = y_pinned.to(dev, non_blocking=True)
+        return float(self.step(x, y).item())
+
+    # the capture warm-up and the capture itself run the step body for real: undo their effect on the
+    # parameters, optimiser state and BatchNorm buffers so that step k of a graph run equals step k eagerly
+    def _snapshot(self):
+        ts = [p.detach() for p in self.model.parameters()] + [b for b in self.model.buffers()]
+        for p in self.model.parameters():
+            st = self.opt.state.get(p, {})
+            ts += [st[k] for k in ("exp_avg", "exp_avg_sq") if k in st]
+        return [(t, t.clone()) for t in ts], {p: dict(self.opt.state.get(p, {})) for p in self.model.parameters()}
+
+    def _restore(self, state):
+        saved, opt_state = state
+        with torch.no_grad():
+            for t, c in saved:
+                t.copy_(c)
+            for p in self.model.parameters():
+                st = self.opt.state.get(p)
+                if st is None:
+                    continue
+                if not opt_state[p]:
+                    # state was created during the warm-up: reset it to Adam's initial state
+                    st["exp_avg"].zero_()
+                    st["exp_avg_sq"].zero_()
+                st["step"] = torch.tensor(float(self.step_count))

@@ -141,10 +141,12 @@ int clk_argmax_confusion(const float* logits, const int64_t* labels, long long P
 
 /* ---- optimiser: torch.optim.Adam step (trainer.py:108-110,176) over a table of tensors ----
  * tensors: device array of {float* p; const float* g; float* m; float* v; int64 numel};
- * blocks: device array of int2 {tensor index, chunk index}; bc1 = 1-b1^t, bc2_sqrt = sqrt(1-b2^t). */
+ * blocks: device array of int2 {tensor index, chunk index}; bc1 = 1-b1^t, bc2_sqrt = sqrt(1-b2^t).
+ * hyper_dev (optional): device float[4] {lr, bc1, bc2_sqrt, gscale} overriding the by-value scalars, so a
+ * captured CUDA graph of the step can be replayed with a new step count / learning rate. */
 int clk_adam_multi_tensor(const void* tensors, const void* blocks, int nblocks, int chunk, float lr,
                           float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale,
-                          clk_stream_t st);
+                          const float* hyper_dev, clk_stream_t st);
 
 #ifdef __cplusplus
 }
