@@ -129,10 +129,40 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+launch_count = 0      # clk_* kernel launches issued by this process (bench.py reports it)
+_profile = None       # when a list: (name, start_event, end_event) per launch, for per-kernel timing
+
+
+def start_profile():
+    global _profile
+    _profile = []
+
+
+def stop_profile():
+    """returns {entry point: (launches, total_ms)} measured with CUDA events on the launching stream."""
+    global _profile
+    rec, _profile = _profile, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in rec or []:
+        n, ms = out.get(name, (0, 0.0))
+        out[name] = (n + 1, ms + e0.elapsed_time(e1))
+    return out
+
+
 def call(name, *args):
     """Call a clk_* kernel entry point: tensors -> pointers, appends the current stream, checks status."""
+    global launch_count
     lib = load()
     conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a) for a in args]
-    rc = getattr(lib, name)(*conv, _stream())
+    if _profile is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*conv, _stream())
+        e1.record()
+        _profile.append((name, e0, e1))
+    else:
+        rc = getattr(lib, name)(*conv, _stream())
+    launch_count += 1
     if rc != CLK_OK:
         raise ClkError(rc, last_error())

@@ -566,8 +566,8 @@ int clk_confusion_matrix(const int64_t* target, const int64_t* pred, long long n
   if (nc > 36) return fail(CLK_E_UNSUPPORTED_SHAPE, "confusion_matrix: nc must be <= 36 (nc=%d)", nc);
   if (n == 0) return CLK_OK;
   if (!target || !pred) return fail(CLK_E_BADARG, "confusion_matrix: null input");
-  if ((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(pred)) & 15)
-    return fail(CLK_E_BADARG, "confusion_matrix: inputs must be 16-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(pred)) & 7)
+    return fail(CLK_E_BADARG, "confusion_matrix: inputs must be 8-byte aligned int64 arrays");
   return cuda_status(confusion_matrix(reinterpret_cast<const long long*>(target),
                                       reinterpret_cast<const long long*>(pred), n, nc,
                                       reinterpret_cast<long long*>(conf), err_flag, S(st)),

@@ -795,8 +795,9 @@ __global__ void __launch_bounds__(kHistThreads)
   for (int i = threadIdx.x; i < copies * nbins; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   unsigned int* mine = sh + (threadIdx.x >> 5) * nbins;
-  // two int64 per 16-byte vector
-  const long long nvec = n / 2;
+  // two int64 per 16-byte vector when both inputs are 16-byte aligned, scalar loads otherwise
+  const bool vec = ((reinterpret_cast<uintptr_t>(target) | reinterpret_cast<uintptr_t>(pred)) & 15) == 0;
+  const long long nvec = vec ? n / 2 : 0;
   const longlong2* t2 = reinterpret_cast<const longlong2*>(target);
   const longlong2* p2 = reinterpret_cast<const longlong2*>(pred);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
@@ -811,8 +812,9 @@ __global__ void __launch_bounds__(kHistThreads)
       else if (err_flag) *err_flag = 1;
     }
   }
-  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
-    const long long t = target[n - 1], p = pred[n - 1];
+  for (long long i = 2 * nvec + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long t = target[i], p = pred[i];
     if (t >= 0 && t < nc) {
       if (p >= 0 && p < nc) atomicAdd(mine + t * nc + p, 1u);
       else if (err_flag) *err_flag = 1;

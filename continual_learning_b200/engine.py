@@ -227,9 +227,11 @@ class UNetEngine:
         ops.f64_to_f32(self.tdbias[j], self.gview[mod.bias])
         return ops.convT_dgrad(dy, self.twd[j])
 
-    def backward(self, dlogits):
+    def backward(self, dlogits, after_decoder=None):
         """dlogits: bf16 [N, H, W, 64] (columns >= num_classes zero). Fills the flat gradient buffer and
-        returns the per-parameter gradient views (PyTorch layouts) in `module.parameters()` order."""
+        returns the per-parameter gradient views (PyTorch layouts) in `module.parameters()` order.
+        `after_decoder()` is called once the head + decoder gradients are final (85 % of the bytes), so a
+        data-parallel caller can start reducing them while the encoder backward still runs."""
         U = self.units
         nc = self.m.num_classes
         self.acc_b.zero_()
@@ -253,6 +255,8 @@ class UNetEngine:
                 skip_grads.append(dskip)  # enc2, enc3, enc4 in that order
             else:
                 dpool = dskip  # gradient of the centre pool output
+        if after_decoder is not None:
+            after_decoder()
         # encoder, deepest first: enc4 (U[7]) .. enc1 (U[1])
         for lvl, k in ((3, 7), (2, 5), (1, 3), (0, 1)):
             dz = ops.maxpool_bwd_add(dpool, U[k].idx, skip_grads[lvl])

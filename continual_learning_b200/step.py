@@ -24,6 +24,8 @@ class TrainStep:
         self.graph = None
         self.shape = None
         self.step_count = 0
+        self.launches_per_step = 0
+        self._graph_ptr = None
         self._opt_ready = False
 
     # ------------------------------------------------------------------ one eager step on device tensors
@@ -38,15 +40,17 @@ class TrainStep:
         self.loss_acc.zero_()
         ops.ce_kd_loss(logits, y, old_logits, T=self.T, lam=self.lam, dlogits=self.dlogits, loss_acc=self.loss_acc,
                        err_flag=self.err_flag)
-        views = eng.backward(self.dlogits)
+        hook = None
+        if self.comm is not None:
+            hook = lambda: self.comm.start_decoder(eng.G)
+        views = eng.backward(self.dlogits, after_decoder=hook)
         eng.release()
-        if not self._opt_ready:
-            for p, v in zip(eng.params, views):
+        for p, v in zip(eng.params, views):
+            if p.grad is not v:  # first step, or the module was moved (.cpu()/.cuda() in save_network)
                 p.grad = v
-            self._opt_ready = True
         gscale = 1.0
         if self.comm is not None:
-            self.comm.all_reduce(eng.G)
+            self.comm.finish(eng.G)
             gscale = 1.0 / self.comm.world_size
         self.opt.step(grad_scale=gscale, hyper_dev=self.hyper)
 
@@ -60,7 +64,6 @@ class TrainStep:
         self.loss_acc = torch.zeros(2, device=dev, dtype=torch.float64)
         self.err_flag = torch.zeros(1, device=dev, dtype=torch.int32)
         self.hyper = torch.zeros(4, device=dev, dtype=torch.float32)
-        self.hyper_host = torch.zeros(4, dtype=torch.float32).pin_memory()
         self.npix = n * h * w
         self.graph = None
         self._opt_ready = False
@@ -68,9 +71,8 @@ class TrainStep:
     def _set_hyper(self):
         gs = 1.0 if self.comm is None else 1.0 / self.comm.world_size
         vals = self.opt.hyper_values(self.step_count + 1, grad_scale=gs)
-        for i, v in enumerate(vals):
-            self.hyper_host[i] = v
-        self.hyper.copy_(self.hyper_host, non_blocking=True)
+        # pageable source: the driver stages it before returning, so the host may run ahead safely
+        self.hyper.copy_(torch.tensor(vals, dtype=torch.float32))
 
     def step(self, x, y):
         """x fp32 [B,3,H,W], y int64 [B,H,W], both on the device. Returns the loss as a 0-dim fp64 device tensor."""
@@ -82,6 +84,9 @@ class TrainStep:
         else:
             self.x_static.copy_(x, non_blocking=True)
             self.y_static.copy_(y, non_blocking=True)
+            ptr = self.model.engine.params[0].data_ptr() if self.model.engine._dev is not None else None
+            if self.graph is not None and ptr != self._graph_ptr:
+                self.graph = None  # parameters were re-allocated (module moved): capture again
             if self.graph is None:
                 # warm-up eagerly on a side stream (allocator + lazy initialisation), then capture
                 state = self._snapshot()
@@ -96,9 +101,13 @@ class TrainStep:
                 if self.old is not None:
                     self.old.engine._wver = None
                 g = torch.cuda.CUDAGraph()
+                from . import _lib
+                n0 = _lib.launch_count
                 with torch.cuda.graph(g):
                     self._body(self.x_static, self.y_static)
+                self.launches_per_step = _lib.launch_count - n0  # clk_* kernels replayed per graph launch
                 self.graph = g
+                self._graph_ptr = self.model.engine.params[0].data_ptr()
                 self._restore(state)
             self.graph.replay()
         self.step_count += 1
