@@ -18,6 +18,7 @@ thread_local char g_err[512] = "";
 int g_fprop_bn = 0;
 int g_wgrad_ksplit = 0;
 int g_wgrad_bn = 64;
+int g_wgrad_v2 = 1;
 int g_num_sms_api = 148;
 
 int fail(int code, const char* fmt, ...) {
@@ -221,6 +222,7 @@ int clk_set_tuning(const char* key, int value) {
   if (strcmp(key, "fprop_bn") == 0) g_fprop_bn = value;
   else if (strcmp(key, "wgrad_ksplit") == 0) g_wgrad_ksplit = value;
   else if (strcmp(key, "wgrad_bn") == 0) g_wgrad_bn = (value == 128 ? 128 : 64);
+  else if (strcmp(key, "wgrad_v2") == 0) g_wgrad_v2 = value;
   else return fail(CLK_E_BADARG, "unknown tuning key %s", key);
   return CLK_OK;
 }
@@ -316,6 +318,32 @@ int clk_conv3x3_wgrad(const void* dy, int Cout, const void* x0, int C0, const vo
   if (!dy || !x0 || !dw || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "conv3x3_wgrad: bad args");
   if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (x1 == nullptr) != (C1 == 0))
     return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_wgrad: channels must be multiples of 64");
+  if (g_wgrad_v2) {
+    // halo variant: (64 cin) x (64 cout) x 9 taps per CTA, 16x8-pixel K tiles
+    Wgrad9Params q;
+    memset(&q, 0, sizeof(q));
+    q.N = N; q.H = H; q.W = W;
+    q.tiles_w = (W + 7) / 8;
+    q.tiles_h = (H + 15) / 16;
+    q.tiles_total = N * q.tiles_h * q.tiles_w;
+    q.cin_slabs = (C0 + C1) / 64;
+    q.split_slabs = C0 / 64;
+    q.cout_tiles = Cout / 64;
+    q.Cin = C0 + C1;
+    q.Cout = Cout;
+    q.out = dw;
+    const int base = q.cin_slabs * q.cout_tiles;
+    int ks = g_wgrad_ksplit > 0 ? g_wgrad_ksplit : (g_num_sms_api / base);
+    if (ks < 1) ks = 1;
+    if (ks > q.tiles_total) ks = q.tiles_total;
+    q.ksplit = ks;
+    CUtensorMap u, t0, t1;
+    CHECK_RC(map_nhwc(&u, dy, N, H, W, Cout, 8, 16, 1));
+    CHECK_RC(map_nhwc(&t0, x0, N, H, W, C0, 16, 18, 1));
+    if (x1) CHECK_RC(map_nhwc(&t1, x1, N, H, W, C1, 16, 18, 1));
+    else t1 = t0;
+    return cuda_status(launch_wgrad9(u, t0, t1, q, S(st)), "conv3x3_wgrad(halo)");
+  }
   WgradParams p;
   memset(&p, 0, sizeof(p));
   geom_nhwc(p.g, N, H, W, 64);

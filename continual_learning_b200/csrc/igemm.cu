@@ -426,6 +426,146 @@ __global__ void __launch_bounds__(kThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------------
+// WGRAD9 (conv3x3, all nine taps per CTA, halo reuse).
+//   D[pair p][row = 64*(tap - 2p) + ci][co] = sum_px X[px (+) tap][ci] * dY[px][co],  tap in {2p, 2p+1}
+//   A operand = X halo tile (MN-major, M = 128 = two 64-channel "slabs" that are the SAME 64 channels
+//   read through two different tap windows: LBO = byte distance between the two windows),
+//   B operand = dY tile (MN-major, N = 64).  K = 128 pixels (16 rows x 8) per stage, 8 MMAs of K=16.
+constexpr int kW9Stages = 4;
+constexpr int kW9UBytes = 128 * 128;      // [16x8 px][64 ch]
+constexpr int kW9TBytes = 18 * 16 * 128;  // [18 rows][16 px][64 ch]; row pitch 16 px = 2048 B
+constexpr int kW9StageBytes = kW9UBytes + kW9TBytes;
+
+__global__ void __launch_bounds__(kThreads, 1)
+    igemm_wgrad9_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT0,
+                        const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ Wgrad9Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kW9Stages * kW9StageBytes);
+  uint64_t* empty = full + kW9Stages;
+  uint64_t* tmem_full = empty + kW9Stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int co_tile = blockIdx.x % p.cout_tiles;
+  const int ci_slab = blockIdx.x / p.cout_tiles;
+  const int per = (p.tiles_total + p.ksplit - 1) / p.ksplit;
+  const int t_begin = blockIdx.y * per;
+  const int num_kb = min(p.tiles_total, t_begin + per) - t_begin;
+  if (num_kb <= 0) return;
+  constexpr uint32_t TMEM_COLS = 512;  // 5 tap pairs x 64 columns
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kW9Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&mapU);
+    tma_prefetch_desc(&mapT0);
+    tma_prefetch_desc(&mapT1);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const bool src0 = ci_slab < p.split_slabs;
+      const CUtensorMap* mapT = src0 ? &mapT0 : &mapT1;
+      const int ct = (src0 ? ci_slab : ci_slab - p.split_slabs) * 64;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kW9Stages;
+        const uint32_t ph = (kb / kW9Stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], kW9StageBytes);
+        const int tile = t_begin + kb;
+        const int tx = tile % p.tiles_w;
+        const int r = tile / p.tiles_w;
+        const int ty = r % p.tiles_h;
+        const int n = r / p.tiles_h;
+        uint8_t* sU = smem + s * kW9StageBytes;
+        tma_load_5d(sU, &mapU, &full[s], co_tile * 64, tx * 8, ty * 16, n, 0);
+        tma_load_5d(sU + kW9UBytes, mapT, &full[s], ct, tx * 8 - 1, ty * 16 - 1, n, 0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kW9Stages;
+        const uint32_t ph = (kb / kW9Stages) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t u = smem_u32(smem + s * kW9StageBytes);
+        const uint32_t t = u + kW9UBytes;
+#pragma unroll
+        for (int pr = 0; pr < 5; ++pr) {
+          const int ta = 2 * pr, tb = (pr < 4) ? 2 * pr + 1 : 2 * pr;  // pair 4: tap 8 + a harmless shifted copy
+          const uint32_t offa = ((ta / 3) * 16 + (ta % 3)) * 128;
+          const uint32_t offb = (pr < 4) ? ((tb / 3) * 16 + (tb % 3)) * 128 : offa + 128;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            umma_bf16(tmem_base + pr * 64, umma_smem_desc(t + offa + k * 4096, offb - offa, 2048),
+                      umma_smem_desc(u + k * 2048, 8192, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ci = ci_slab * 64 + (row & 63);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    for (int pr = 0; pr < 5; ++pr) {
+      const int tap = 2 * pr + (row >> 6);
+      float* obase = p.out + (static_cast<size_t>(tap) * p.Cout + co_tile * 64) * p.Cin + ci;
+#pragma unroll 1
+      for (int chunk = 0; chunk < 2; ++chunk) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + pr * 64 + chunk * 32, v);
+        tmem_ld_wait();
+        if (tap < 9) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            atomicAdd(obase + static_cast<size_t>(chunk * 32 + j) * p.Cin, __uint_as_float(v[j]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+cudaError_t launch_wgrad9(const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
+                          const Wgrad9Params& p, cudaStream_t st) {
+  const int smem = kW9Stages * kW9StageBytes + (2 * kW9Stages + 1) * 8 + 16 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  dim3 grid(p.cin_slabs * p.cout_tiles, p.ksplit);
+  igemm_wgrad9_kernel<<<grid, kThreads, smem, st>>>(u, t0, t1, p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 template <int BN, int STAGES>
 static constexpr int fprop_smem_bytes() {

@@ -69,6 +69,21 @@ cudaError_t launch_fprop(int BN, int out_is_f32, const CUtensorMap& a0, const CU
                          cudaStream_t st);
 cudaError_t launch_wgrad(int BN, const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
                          const WgradParams& p, cudaStream_t st);
-cudaError_t igemm_set_attributes();
+
+// conv3x3 weight gradient, halo variant: one CTA owns (64 input channels) x (64 output channels) x ALL
+// nine taps; per 16x8-pixel K tile it loads the dY tile once and one 18x16-pixel halo tile of X, and
+// reads the nine shifted windows of the halo through row-shifted UMMA descriptors (two taps stacked in
+// the M=128 rows of each MMA).
+struct Wgrad9Params {
+  int N, H, W;
+  int tiles_w, tiles_h, tiles_total;  // 16 (h) x 8 (w) pixel K tiles
+  int cin_slabs, split_slabs;         // 64-channel slabs of X over both sources / in source 0
+  int cout_tiles;                     // 64-channel tiles of dY
+  int ksplit;
+  int Cin, Cout;
+  float* out;                         // [9][Cout][Cin] fp32, red.add accumulated (caller zeroes)
+};
+cudaError_t launch_wgrad9(const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
+                          const Wgrad9Params& p, cudaStream_t st);
 
 }  // namespace clk
