@@ -72,9 +72,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([t.strip() for t in line.split(",")])
+            self.rows.append((time.time(), [t.strip() for t in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -84,7 +84,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts_, r in self.rows:
+            if t_begin is not None and not (t_begin <= ts_ <= t_end):
+                continue  # keep only the samples taken inside the timed region
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -185,22 +187,24 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()  # nvidia-smi needs a moment to start: launch it before the warm-up, filter by time later
     for i in range(warmup):
         ts.step(*devb[i % nb])
     barrier()
     launches0 = _lib.launch_count
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    w_begin = time.time()
     e0.record()
     for i in range(args.steps):
         loss = ts.step(*devb[i % nb])
     e1.record()
     barrier()
+    w_end = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(w_begin, w_end) if rank == 0 else None
     last_loss = float(loss)
     if ts.graph is not None:
         launches = ts.launches_per_step * args.steps
@@ -222,6 +226,7 @@ def run_b200(args):
         ts.step_host(*pinned[i % nb])
     e1.record()
     barrier()
+    wall_e2e = time.perf_counter() - t0
     ms_e2e = e0.elapsed_time(e1)
     t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
     if world > 1:
@@ -271,7 +276,7 @@ def run_b200(args):
         "model_tflops": value * GFLOP_PER_IMG_TRAIN / 1e3 / world,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": (time.perf_counter() - t0) * 1e3 / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e * 1e3 / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "igemm_fprop_kernel/igemm_wgrad_kernel (all tcgen05 conv/convT/1x1 launches of a step)",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
@@ -289,7 +294,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")

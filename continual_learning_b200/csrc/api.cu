@@ -19,6 +19,8 @@ int g_fprop_bn = 0;
 int g_wgrad_ksplit = 0;
 int g_wgrad_bn = 64;
 int g_wgrad_v2 = 1;
+int g_conv3_v2 = 1;
+int g_conv3_min_hw = 2048;  // halo kernel for images with at least this many pixels; smaller maps use the generic kernel (BN up to 256)
 int g_num_sms_api = 148;
 
 int fail(int code, const char* fmt, ...) {
@@ -223,6 +225,8 @@ int clk_set_tuning(const char* key, int value) {
   else if (strcmp(key, "wgrad_ksplit") == 0) g_wgrad_ksplit = value;
   else if (strcmp(key, "wgrad_bn") == 0) g_wgrad_bn = (value == 128 ? 128 : 64);
   else if (strcmp(key, "wgrad_v2") == 0) g_wgrad_v2 = value;
+  else if (strcmp(key, "conv3_v2") == 0) g_conv3_v2 = value;
+  else if (strcmp(key, "conv3_min_hw") == 0) g_conv3_min_hw = value;
   else return fail(CLK_E_BADARG, "unknown tuning key %s", key);
   return CLK_OK;
 }
@@ -261,6 +265,31 @@ int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void
   if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (x1 == nullptr) != (C1 == 0))
     return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_fprop: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)",
                 C0, C1, Cout);
+  if (g_conv3_v2 && (H * W >= g_conv3_min_hw || g_conv3_v2 == 2)) {
+    Conv3Params q;
+    memset(&q, 0, sizeof(q));
+    q.N = N; q.H = H; q.W = W;
+    q.tiles_w = (W + 15) / 16;
+    q.tiles_h = (H + 15) / 16;
+    q.m_tiles = N * q.tiles_h * q.tiles_w;
+    const int BNq = (Cout % 128 == 0 && g_fprop_bn != 64) ? 128 : 64;
+    q.n_tiles = Cout / BNq;
+    q.kc0 = C0 / 64;
+    q.kc1 = C1 / 64;
+    q.n_store = Cout;
+    q.dst0 = y;
+    q.ldc0 = Cout;
+    q.bias = bias;
+    q.relu = relu;
+    q.stat_sum = stat_sum;
+    q.stat_sq = stat_sq;
+    CUtensorMap a0, a1, b;
+    CHECK_RC(map_nhwc(&a0, x0, N, H, W, C0, 24, 18, 1));
+    if (x1) CHECK_RC(map_nhwc(&a1, x1, N, H, W, C1, 24, 18, 1));
+    else a1 = a0;
+    CHECK_RC(map_weights(&b, w, 9, Cout, C0 + C1, BNq));
+    return cuda_status(launch_conv3(BNq, a0, a1, b, q, g_num_sms_api, S(st)), "conv3x3_fprop(halo)");
+  }
   FpropParams p;
   memset(&p, 0, sizeof(p));
   geom_nhwc(p.g, N, H, W, 128);
@@ -289,6 +318,30 @@ int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C
   if (!dy || !wd || !dx0 || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "conv3x3_dgrad: bad args");
   if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (dx1 == nullptr) != (C1 == 0))
     return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_dgrad: channels must be multiples of 64");
+  if (g_conv3_v2 && (H * W >= g_conv3_min_hw || g_conv3_v2 == 2)) {
+    Conv3Params q;
+    memset(&q, 0, sizeof(q));
+    const int Cin2 = C0 + C1;
+    q.N = N; q.H = H; q.W = W;
+    q.tiles_w = (W + 15) / 16;
+    q.tiles_h = (H + 15) / 16;
+    q.m_tiles = N * q.tiles_h * q.tiles_w;
+    int BNq = (Cin2 % 128 == 0 && g_fprop_bn != 64) ? 128 : 64;
+    if (C1 > 0 && (C0 % BNq || C1 % BNq)) BNq = 64;
+    q.n_tiles = Cin2 / BNq;
+    q.kc0 = Cout / 64;
+    q.kc1 = 0;
+    q.n_store = Cin2;
+    q.split_c = C1 > 0 ? C0 : 0;
+    q.dst0 = dx0;
+    q.ldc0 = C0;
+    q.dst1 = dx1;
+    q.ldc1 = C1;
+    CUtensorMap a0, b;
+    CHECK_RC(map_nhwc(&a0, dy, N, H, W, Cout, 24, 18, 1));
+    CHECK_RC(map_weights(&b, wd, 9, Cin2, Cout, BNq));
+    return cuda_status(launch_conv3(BNq, a0, a0, b, q, g_num_sms_api, S(st)), "conv3x3_dgrad(halo)");
+  }
   FpropParams p;
   memset(&p, 0, sizeof(p));
   geom_nhwc(p.g, N, H, W, 128);

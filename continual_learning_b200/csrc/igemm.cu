@@ -566,6 +566,282 @@ cudaError_t launch_wgrad9(const CUtensorMap& u, const CUtensorMap& t0, const CUt
 }
 
 // ------------------------------------------------------------------------------------------
+// CONV3 (conv3x3 forward / dgrad, halo variant, persistent).
+//   super tile = 16 x 16 output pixels of one image = two M=128 sub tiles (columns 0-7 / 8-15);
+//   A ring (2 stages): one [18 rows][24 px][64 ch] halo tile per 64-channel K chunk (row pitch 3072 B);
+//   B ring (NB stages): one [BN][64] weight tile per (chunk, tap);
+//   tap (r, s) of sub tile j reads the halo through a descriptor starting at ((r*24 + s + 8j) * 128) B,
+//   SBO = 3072 (the hardware swizzle is a function of the absolute smem address, so whole-row shifts of
+//   the start address stay consistent with what TMA wrote);
+//   TMEM: 2 accumulator stages x 2 sub tiles x BN columns, epilogue of tile i overlaps main loop of i+1.
+constexpr int kC3ABytes = 18 * 24 * 128;
+constexpr int kC3Scratch = 8 * 32 * 33 * 4;
+constexpr int kC3Threads = 64 + 256;  // TMA warp, MMA warp, 8 epilogue warps (4 per sub tile)
+constexpr int kC3EpiThreads = 256;
+template <int BN>
+struct C3Cfg {
+  static constexpr int NB = (BN == 128) ? 5 : 8;
+  static constexpr int BBytes = BN * 128;
+  static constexpr int Smem = 2 * kC3ABytes + NB * BBytes + kC3Scratch + 3 * BN * 4 + (8 + 2 * NB) * 8 + 16 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kC3Threads, 1)
+    igemm_conv3_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                       const __grid_constant__ CUtensorMap mapB, const __grid_constant__ Conv3Params p) {
+  constexpr int NB = C3Cfg<BN>::NB;
+  constexpr int B_BYTES = C3Cfg<BN>::BBytes;
+  constexpr uint32_t TMEM_COLS = 4 * BN;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 2 * kC3ABytes;
+  float* scratch_all = reinterpret_cast<float*>(sB + NB * B_BYTES);
+  float* s_sum = scratch_all + 8 * 32 * 33;
+  float* s_sq = s_sum + BN;
+  float* s_bias = s_sq + BN;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_bias + BN);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* acc_full = a_empty + 2;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* b_full = acc_empty + 2;
+  uint64_t* b_empty = b_full + NB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + NB);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kc = p.kc0 + p.kc1;
+  const int total = p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 8);
+    }
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 3 * BN; i += kC3Threads) s_sum[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (elect_one()) {
+      uint32_t ia = 0, ib = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m = t % p.m_tiles, nt = t / p.m_tiles;
+        const int tx = m % p.tiles_w;
+        const int r = m / p.tiles_w;
+        const int ty = r % p.tiles_h;
+        const int n = r / p.tiles_h;
+        for (int ch = 0; ch < kc; ++ch) {
+          const uint32_t sa = ia & 1, pa = (ia >> 1) & 1;
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_arrive_expect_tx(&a_full[sa], kC3ABytes);
+          if (ch < p.kc0)
+            tma_load_5d(sA + sa * kC3ABytes, &mapA0, &a_full[sa], ch * 64, tx * 16 - 1, ty * 16 - 1, n, 0);
+          else
+            tma_load_5d(sA + sa * kC3ABytes, &mapA1, &a_full[sa], (ch - p.kc0) * 64, tx * 16 - 1, ty * 16 - 1, n, 0);
+          ++ia;
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t sb = ib % NB, pb = (ib / NB) & 1;
+            mbar_wait(&b_empty[sb], pb ^ 1);
+            mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
+            tma_load_3d(sB + sb * B_BYTES, &mapB, &b_full[sb], ch * 64, nt * BN, tap);
+            ++ib;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      uint32_t ia = 0, ib = 0, it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const uint32_t acc = it & 1, pacc = (it >> 1) & 1;
+        mbar_wait(&acc_empty[acc], pacc ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * 2 * BN;
+        for (int ch = 0; ch < kc; ++ch) {
+          const uint32_t sa = ia & 1, pa = (ia >> 1) & 1;
+          mbar_wait(&a_full[sa], pa);
+          const uint32_t abase = smem_u32(sA + sa * kC3ABytes);
+#pragma unroll 1
+          for (int tr = 0; tr < 3; ++tr) {
+#pragma unroll 1
+            for (int tsx = 0; tsx < 3; ++tsx) {
+              const uint32_t sb = ib % NB, pb = (ib / NB) & 1;
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              const uint32_t a = abase + (tr * 24 + tsx) * 128;
+              const uint32_t b = smem_u32(sB + sb * B_BYTES);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(d0 + j * BN, umma_smem_desc(a + j * 1024 + k * 32, 16, 3072),
+                            umma_smem_desc(b + k * 32, 16, 1024), idesc, (ch | tr | tsx | k) != 0 ? 1u : 0u);
+                }
+              }
+              umma_commit(&b_empty[sb]);
+              ++ib;
+            }
+          }
+          umma_commit(&a_empty[sa]);
+          ++ia;
+        }
+        umma_commit(&acc_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------ epilogue (warps 2..9: quadrant = warp % 4, sub tile = (warp-2)/4)
+    const int q = warp & 3;
+    const int j = (warp - 2) >> 2;
+    const int mrow = q * 32 + lane;
+    const int etid = threadIdx.x - 64;
+    const bool do_stats = p.stat_sum != nullptr;
+    float* scratch = scratch_all + (warp - 2) * (32 * 33);
+    uint32_t it = 0;
+    int bias_nt = -1;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int m = t % p.m_tiles, nt = t / p.m_tiles;
+      const int tx = m % p.tiles_w;
+      const int r = m / p.tiles_w;
+      const int ty = r % p.tiles_h;
+      const int n = r / p.tiles_h;
+      const int n0 = nt * BN;
+      const uint32_t acc = it & 1, pacc = (it >> 1) & 1;
+      if (nt != bias_nt) {  // (uniform across the epilogue warps) stage this N tile's bias in smem
+        named_bar_sync(2, kC3EpiThreads);
+        for (int i = etid; i < BN; i += kC3EpiThreads)
+          s_bias[i] = (p.bias != nullptr && n0 + i < p.n_store) ? p.bias[n0 + i] : 0.f;
+        named_bar_sync(2, kC3EpiThreads);
+        bias_nt = nt;
+      }
+      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.dst0);
+      int ld = p.ldc0, colbase = n0;
+      if (p.split_c > 0 && n0 >= p.split_c) {
+        dst = reinterpret_cast<__nv_bfloat16*>(p.dst1);
+        ld = p.ldc1;
+        colbase = n0 - p.split_c;
+      }
+      const int h = ty * 16 + (mrow >> 3);
+      const int w = tx * 16 + j * 8 + (mrow & 7);
+      const bool valid = h < p.H && w < p.W;
+      __nv_bfloat16* drow = dst + (valid ? (static_cast<long long>(n) * p.H + h) * p.W + w : 0) * ld + colbase;
+      mbar_wait(&acc_full[acc], pacc);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 2 * BN + j * BN + chunk * 32, v);
+        tmem_ld_wait();
+        const bool in_store = (n0 + chunk * 32) < p.n_store;
+        uint32_t pk[16];
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + chunk * 32);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const float4 bb = b4[jj];
+          float x0 = __uint_as_float(v[4 * jj]) + bb.x, x1 = __uint_as_float(v[4 * jj + 1]) + bb.y;
+          float x2 = __uint_as_float(v[4 * jj + 2]) + bb.z, x3 = __uint_as_float(v[4 * jj + 3]) + bb.w;
+          if (p.relu) {
+            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+          }
+          pk[2 * jj] = pack_bf16x2(x0, x1);
+          pk[2 * jj + 1] = pack_bf16x2(x2, x3);
+        }
+        if (valid && in_store) {
+          uint4* o = reinterpret_cast<uint4*>(drow + chunk * 32);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            o[jj] = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+        }
+        if (do_stats) {
+          __syncwarp();
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            scratch[lane * 33 + 2 * jj] = valid ? bf16lo_to_f32(pk[jj]) : 0.f;
+            scratch[lane * 33 + 2 * jj + 1] = valid ? bf16hi_to_f32(pk[jj]) : 0.f;
+          }
+          __syncwarp();
+          float s = 0.f, sq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = scratch[i * 33 + lane];
+            s += x;
+            sq = fmaf(x, x, sq);
+          }
+          atomicAdd(&s_sum[chunk * 32 + lane], s);
+          atomicAdd(&s_sq[chunk * 32 + lane], sq);
+        }
+      }
+      // accumulator stage drained: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (do_stats) {
+        named_bar_sync(1, kC3EpiThreads);
+        for (int i = etid; i < BN; i += kC3EpiThreads) {
+          if (n0 + i < p.n_store) {
+            atomicAdd(&p.stat_sum[n0 + i], static_cast<double>(s_sum[i]));
+            atomicAdd(&p.stat_sq[n0 + i], static_cast<double>(s_sq[i]));
+          }
+          s_sum[i] = 0.f;
+          s_sq[i] = 0.f;
+        }
+        named_bar_sync(1, kC3EpiThreads);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN>
+static cudaError_t launch_conv3_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                                  const Conv3Params& p, int num_sms, cudaStream_t st) {
+  constexpr int smem = C3Cfg<BN>::Smem;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_conv3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  int grid = p.m_tiles * p.n_tiles;
+  if (grid > num_sms) grid = num_sms;
+  igemm_conv3_kernel<BN><<<grid, kC3Threads, smem, st>>>(a0, a1, b, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv3(int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                         const Conv3Params& p, int num_sms, cudaStream_t st) {
+  if (BN == 128) return launch_conv3_t<128>(a0, a1, b, p, num_sms, st);
+  if (BN == 64) return launch_conv3_t<64>(a0, a1, b, p, num_sms, st);
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 template <int BN, int STAGES>
 static constexpr int fprop_smem_bytes() {

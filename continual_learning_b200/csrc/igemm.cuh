@@ -86,4 +86,23 @@ struct Wgrad9Params {
 cudaError_t launch_wgrad9(const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
                           const Wgrad9Params& p, cudaStream_t st);
 
+// conv3x3 forward / dgrad, halo variant: persistent CTAs, 16x16-pixel super tile (two M=128 sub tiles),
+// ONE 18x24-pixel halo load per 64-channel chunk feeds all nine taps through row-shifted descriptors,
+// weights stream through their own ring, two TMEM accumulator stages overlap epilogue and main loop.
+struct Conv3Params {
+  int N, H, W;
+  int tiles_w, tiles_h, m_tiles, n_tiles;
+  int kc0, kc1;        // 64-channel chunks of source 0 / source 1
+  int n_store, split_c;
+  void* dst0;
+  void* dst1;
+  int ldc0, ldc1;
+  const float* bias;
+  int relu;
+  double* stat_sum;
+  double* stat_sq;
+};
+cudaError_t launch_conv3(int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                         const Conv3Params& p, int num_sms, cudaStream_t st);
+
 }  // namespace clk

@@ -104,5 +104,6 @@ def metrics_case(name):
 if __name__ == "__main__":
     unet_case("unet_b1_32x32", 0, 1, 1, 32, 32)
     unet_case("unet_b2_48x32_c7", 2, 4, 2, 48, 32, num_classes=7)
+    unet_case("unet_b2_64x64", 0, 1, 2, 64, 64)
     traj_case("train_traj_b2_32x32")
     metrics_case("metrics")

@@ -62,10 +62,21 @@ def test_gemm_fprop_bias_relu_stats(ops, P, K, N):
     assert rel(s_sum, q.sum(0)) <= 1e-6 and rel(s_sq, (q * q).sum(0)) <= 1e-6
 
 
+@pytest.fixture(params=["generic", "halo"])
+def conv_kernel(request):
+    """run the conv3x3 forward/dgrad cases through both tcgen05 kernels: the generic per-tap-TMA kernel and the
+    persistent halo kernel (the library picks between them by image size; the knob forces one)."""
+    from continual_learning_b200 import _lib
+    _lib.set_tuning("conv3_v2", 2 if request.param == "halo" else 0)
+    yield request.param
+    _lib.set_tuning("conv3_v2", 1)
+
+
 @pytest.mark.parametrize("n,h,w,c0,c1,co", [(2, 16, 16, 64, 0, 64), (3, 8, 24, 128, 0, 256), (2, 16, 16, 64, 64, 128),
                                               (5, 4, 4, 128, 128, 64), (1, 32, 32, 64, 0, 64), (33, 2, 2, 64, 0, 128),
-                                              (1, 1, 1, 64, 0, 64), (2, 3, 5, 64, 64, 64)])
-def test_conv3x3_fprop_with_folded_concat(ops, n, h, w, c0, c1, co):
+                                              (1, 1, 1, 64, 0, 64), (2, 3, 5, 64, 64, 64), (1, 64, 64, 64, 0, 64),
+                                              (2, 40, 72, 64, 64, 128)])
+def test_conv3x3_fprop_with_folded_concat(ops, conv_kernel, n, h, w, c0, c1, co):
     g = gen(n * 100 + h + co)
     x, wt, b = bfr(rnd(g, n, c0 + c1, h, w)), rnd(g, co, c0 + c1, 3, 3, scale=0.05), rnd(g, co)
     xh = to_nhwc_dev(x)
@@ -82,8 +93,8 @@ def test_conv3x3_fprop_with_folded_concat(ops, n, h, w, c0, c1, co):
 
 
 @pytest.mark.parametrize("n,h,w,c0,c1,co", [(2, 16, 16, 64, 0, 64), (2, 8, 8, 128, 128, 128), (1, 16, 16, 256, 0, 64),
-                                              (2, 6, 10, 64, 64, 64)])
-def test_conv3x3_dgrad_split_destinations(ops, n, h, w, c0, c1, co):
+                                              (2, 6, 10, 64, 64, 64), (1, 64, 48, 128, 0, 64), (2, 33, 17, 64, 64, 128)])
+def test_conv3x3_dgrad_split_destinations(ops, conv_kernel, n, h, w, c0, c1, co):
     g = gen(7 + n + h + co)
     dy, wt = bfr(rnd(g, n, co, h, w)), rnd(g, co, c0 + c1, 3, 3, scale=0.05)
     _, wd = ops.pack_conv3x3(wt.cuda())
@@ -95,7 +106,17 @@ def test_conv3x3_dgrad_split_destinations(ops, n, h, w, c0, c1, co):
 
 @pytest.mark.parametrize("n,h,w,c0,c1,co", [(2, 16, 16, 64, 0, 64), (2, 8, 8, 128, 0, 256), (4, 16, 16, 64, 64, 128),
                                               (8, 32, 32, 64, 0, 64), (3, 4, 4, 128, 0, 128), (2, 5, 3, 64, 0, 64)])
-def test_conv3x3_wgrad_and_unpack(ops, n, h, w, c0, c1, co):
+@pytest.mark.parametrize("variant", ["halo", "generic"])
+def test_conv3x3_wgrad_and_unpack(ops, variant, n, h, w, c0, c1, co):
+    from continual_learning_b200 import _lib
+    _lib.set_tuning("wgrad_v2", 1 if variant == "halo" else 0)
+    try:
+        _check_conv3x3_wgrad(ops, n, h, w, c0, c1, co)
+    finally:
+        _lib.set_tuning("wgrad_v2", 1)
+
+
+def _check_conv3x3_wgrad(ops, n, h, w, c0, c1, co):
     g = gen(11 + n + h + co)
     x, dy = bfr(rnd(g, n, c0 + c1, h, w)), bfr(rnd(g, n, co, h, w, scale=0.1))
     xh = to_nhwc_dev(x)

@@ -10,7 +10,8 @@ from oracle import metrics_ref, step_ref
 from oracle.data import structured_batch
 from oracle.unet_ref import UNetRef, clone_sd, make_state_dict, param_names
 
-CASES = [("unet_b1_32x32", 0, 1, 1, 32, 32, 21), ("unet_b2_48x32_c7", 2, 4, 2, 48, 32, 7)]
+CASES = [("unet_b1_32x32", 0, 1, 1, 32, 32, 21), ("unet_b2_48x32_c7", 2, 4, 2, 48, 32, 7),
+         ("unet_b2_64x64", 0, 1, 2, 64, 64, 21)]
 
 
 @pytest.mark.parametrize("name,seed_w,seed_x,b,h,w,nc", CASES)
