@@ -130,6 +130,7 @@ def _stream():
 
 
 launch_count = 0      # clk_* kernel launches issued by this process (bench.py reports it)
+param_epoch = 0       # bumped by FusedAdam.step: parameters changed behind autograd's version counters
 _profile = None       # when a list: (name, start_event, end_event) per launch, for per-kernel timing
 
 

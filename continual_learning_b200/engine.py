@@ -121,7 +121,7 @@ class UNetEngine:
         self._wver = None
 
     def _pack_weights(self):
-        ver = tuple(p._version for p in self.params) + tuple(p.data_ptr() for p in self.params[:2])
+        ver = (_lib.param_epoch,) + tuple(p._version for p in self.params) + tuple(p.data_ptr() for p in self.params[:2])
         if ver == self._wver:
             return
         for u in self.units:

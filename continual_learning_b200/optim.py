@@ -72,6 +72,7 @@ class FusedAdam(torch.optim.Optimizer):
             t, b, nblocks = self._table(gi, plist)
             _lib.call("clk_adam_multi_tensor", t, b, nblocks, _CHUNK, float(group["lr"]), b1, b2,
                       float(group["eps"]), bc1, bc2_sqrt, float(grad_scale), hyper_dev)
+        _lib.param_epoch += 1  # the kernel wrote the parameters through raw pointers: invalidate packed copies
         return loss
 
     def hyper_values(self, step, grad_scale=1.0, group=0):
