@@ -216,6 +216,7 @@ int clk_query_device(int dev) {
                 prop.major, prop.minor);
   g_num_sms_api = prop.multiProcessorCount;
   set_num_sms(prop.multiProcessorCount);
+  igemm_set_num_sms(prop.multiProcessorCount);
   return CLK_OK;
 }
 
@@ -255,6 +256,19 @@ int clk_unpack_wgrad(const float* D, float* grad, int A, int B, int T, int ldA, 
                      int accumulate, clk_stream_t st) {
   if (!D || !grad || A <= 0 || B <= 0 || T <= 0 || T > 9) return fail(CLK_E_BADARG, "unpack_wgrad: bad args");
   return cuda_status(unpack_wgrad(D, grad, A, B, T, ldA, ldB, alpha, accumulate, S(st)), "unpack_wgrad");
+}
+
+int clk_pack_w_multi(const void* jobs, int njobs, int total_tiles, int max_T, clk_stream_t st) {
+  if (!jobs || njobs <= 0 || total_tiles < 0 || max_T <= 0 || max_T > 9) return fail(CLK_E_BADARG, "pack_w_multi: bad args");
+  return cuda_status(pack_w_multi(jobs, njobs, total_tiles, max_T, S(st)), "pack_w_multi");
+}
+int clk_unpack_wgrad_multi(const void* jobs, int njobs, int total_tiles, int max_T, clk_stream_t st) {
+  if (!jobs || njobs <= 0 || total_tiles < 0 || max_T <= 0 || max_T > 9) return fail(CLK_E_BADARG, "unpack_wgrad_multi: bad args");
+  return cuda_status(unpack_wgrad_multi(jobs, njobs, total_tiles, max_T, S(st)), "unpack_wgrad_multi");
+}
+int clk_f64_to_f32_multi(const void* jobs, int njobs, clk_stream_t st) {
+  if (!jobs || njobs <= 0) return fail(CLK_E_BADARG, "f64_to_f32_multi: bad args");
+  return cuda_status(f64_to_f32_multi(jobs, njobs, S(st)), "f64_to_f32_multi");
 }
 
 // ------------------------------------------------------------------ igemm: conv3x3

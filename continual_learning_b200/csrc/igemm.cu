@@ -15,6 +15,8 @@ namespace clk {
 
 constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
+static int g_fprop_sms = 148;
+void igemm_set_num_sms(int n) { g_fprop_sms = n > 0 ? n : 148; }
 
 // ------------------------------------------------------------------------------------------
 // tile -> TMA base coordinates (coords 1..4; coord 0 is always the channel)
@@ -74,43 +76,53 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* raw) {
 }
 
 // ------------------------------------------------------------------------------------------
-// FPROP: D[128 pixels, BN] = sum_{tap, chunk} A_tile(tap, chunk)[128 x 64] * B(tap, chunk)[BN x 64]^T
+// FPROP (generic): D[128 pixels, BN] = sum_{tap, chunk} A_tile(tap, chunk)[128 x 64] * B(tap, chunk)[BN x 64]^T
+// Persistent: every CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...; the TMA ring keeps running
+// across tiles and two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
+// Used for the 1-tap GEMMs (stem, 1x1 head, head dgrad, ConvTranspose2d forward), the 4-tap ConvTranspose2d
+// dgrad and the conv3x3 layers on small feature maps (BN = 256).
+constexpr int kFpScratch = 4 * 32 * 33 * 4;
+
 template <int BN, int STAGES, typename OutT>
 __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
     igemm_fprop_kernel(const __grid_constant__ CUtensorMap mapA0,
                        const __grid_constant__ CUtensorMap mapA1,
                        const __grid_constant__ CUtensorMap mapB,
-                       const __grid_constant__ FpropParams p) {
+                       const __grid_constant__ FpropParams p, const int m_tiles, const int n_tiles) {
   constexpr int A_BYTES = 128 * 128;
   constexpr int B_BYTES = BN * 128;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_BYTES);
-  uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+  float* scratch_all = reinterpret_cast<float*>(sB + STAGES * B_BYTES);
+  float* s_bias = scratch_all + 4 * 32 * 33;
   float* s_sum = s_bias + BN;
   float* s_sq = s_sum + BN;
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_sq + BN);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * BN;
   const int kc = p.kc0 + p.kc1;
   const int num_kb = p.ntaps * kc;
-  int b1, b2, b3, b4;
-  tile_base(p.g, blockIdx.x, b1, b2, b3, b4);
+  const int total = m_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapA1);
@@ -120,17 +132,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < BN; i += kThreads) {
-    float bv = 0.f;
-    if (p.bias != nullptr) {
-      const int col = n0 + i;
-      if (p.shuffle) bv = p.bias[col % p.cout_q];
-      else if (col < p.n_store) bv = p.bias[col];
-    }
-    s_bias[i] = bv;
-    s_sum[i] = 0.f;
-    s_sq[i] = 0.f;
-  }
+  for (int i = threadIdx.x; i < 3 * BN; i += kThreads) s_bias[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -139,19 +141,24 @@ __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
     if (elect_one()) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
-        const int tap = kb / kc;
-        const int ch = kb - tap * kc;
-        const int c1 = b1 + p.g.t1[tap], c2 = b2 + p.g.t2[tap], c3 = b3 + p.g.t3[tap];
-        if (ch < p.kc0)
-          tma_load_5d(sA + s * A_BYTES, &mapA0, &full[s], ch * 64, c1, c2, c3, b4);
-        else
-          tma_load_5d(sA + s * A_BYTES, &mapA1, &full[s], (ch - p.kc0) * 64, c1, c2, c3, b4);
-        tma_load_3d(sB + s * B_BYTES, &mapB, &full[s], ch * 64, n0, tap);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int n0 = (t / m_tiles) * BN;
+        int b1, b2, b3, b4;
+        tile_base(p.g, t % m_tiles, b1, b2, b3, b4);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], A_BYTES + B_BYTES);
+          const int tap = kb / kc;
+          const int ch = kb - tap * kc;
+          const int c1 = b1 + p.g.t1[tap], c2 = b2 + p.g.t2[tap], c3 = b3 + p.g.t3[tap];
+          if (ch < p.kc0)
+            tma_load_5d(sA + s * A_BYTES, &mapA0, &full[s], ch * 64, c1, c2, c3, b4);
+          else
+            tma_load_5d(sA + s * A_BYTES, &mapA1, &full[s], (ch - p.kc0) * 64, c1, c2, c3, b4);
+          tma_load_3d(sB + s * B_BYTES, &mapB, &full[s], ch * 64, n0, tap);
+        }
       }
     }
     __syncwarp();
@@ -159,113 +166,148 @@ __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
     // ------------------------------------------------ MMA issuer (single thread)
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      uint32_t it = 0, itile = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++itile) {
+        const uint32_t acc = itile & 1, pacc = (itile >> 1) & 1;
+        mbar_wait(&acc_empty[acc], pacc ^ 1);
         tc_fence_after();
-        const uint32_t a = smem_u32(sA + s * A_BYTES);
-        const uint32_t b = smem_u32(sB + s * B_BYTES);
+        const uint32_t d = tmem_base + acc * ACC_COLS;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a = smem_u32(sA + s * A_BYTES);
+          const uint32_t b = smem_u32(sB + s * B_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_bf16(tmem_base, umma_smem_desc(a + k * 32, 16, 1024),
-                    umma_smem_desc(b + k * 32, 16, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            umma_bf16(d, umma_smem_desc(a + k * 32, 16, 1024), umma_smem_desc(b + k * 32, 16, 1024), idesc,
+                      (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
         }
-        umma_commit(&empty[s]);
+        umma_commit(&acc_full[acc]);
       }
-      umma_commit(tmem_full);
     }
     __syncwarp();
   } else {
     // ------------------------------------------------ epilogue: TMEM -> regs -> global
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    int pn = 0, ph_ = 0, pw = 0;
-    long long pix = tile_row_pixel(p.g, b1, b2, b3, b4, m, pn, ph_, pw);
-    const bool valid = pix >= 0;
-    OutT* dst = reinterpret_cast<OutT*>(p.dst0);
-    int ld = p.ldc0;
-    int colbase = n0;
-    if (p.shuffle) {
-      const int qd = n0 / p.cout_q;
-      colbase = n0 - qd * p.cout_q;
-      pix = (static_cast<long long>(pn) * (2 * p.g.H) + 2 * ph_ + (qd >> 1)) * (2 * p.g.W) +
-            2 * pw + (qd & 1);
-    } else if (p.split_c > 0 && n0 >= p.split_c) {
-      dst = reinterpret_cast<OutT*>(p.dst1);
-      ld = p.ldc1;
-      colbase = n0 - p.split_c;
-    }
-    OutT* drow = dst + (valid ? pix : 0) * ld + colbase;
+    const int etid = threadIdx.x - 64;
     const bool do_stats = p.stat_sum != nullptr;
-    float* scratch = reinterpret_cast<float*>(sA) + (warp - 2) * (32 * 33);
-
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int chunk = 0; chunk < BN / 32; ++chunk) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + chunk * 32, v);
-      tmem_ld_wait();
-      float f[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(v[j]) + s_bias[chunk * 32 + j];
-        if (p.relu) x = fmaxf(x, 0.f);
-        f[j] = x;
-      }
-      if constexpr (sizeof(OutT) == 2) {
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-        if (valid && (n0 + chunk * 32) < p.n_store) {
-          uint4* o = reinterpret_cast<uint4*>(drow + chunk * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    float* scratch = scratch_all + (warp - 2) * (32 * 33);
+    uint32_t itile = 0;
+    int bias_nt = -1;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++itile) {
+      const int nt = t / m_tiles;
+      const int n0 = nt * BN;
+      const uint32_t acc = itile & 1, pacc = (itile >> 1) & 1;
+      if (nt != bias_nt) {
+        named_bar_sync(2, kEpiThreads);
+        for (int i = etid; i < BN; i += kEpiThreads) {
+          float bv = 0.f;
+          if (p.bias != nullptr) {
+            const int col = n0 + i;
+            if (p.shuffle) bv = p.bias[col % p.cout_q];
+            else if (col < p.n_store) bv = p.bias[col];
+          }
+          s_bias[i] = bv;
         }
-        if (do_stats) {
+        named_bar_sync(2, kEpiThreads);
+        bias_nt = nt;
+      }
+      int b1, b2, b3, b4;
+      tile_base(p.g, t % m_tiles, b1, b2, b3, b4);
+      int pn = 0, ph_ = 0, pw = 0;
+      long long pix = tile_row_pixel(p.g, b1, b2, b3, b4, m, pn, ph_, pw);
+      const bool valid = pix >= 0;
+      OutT* dst = reinterpret_cast<OutT*>(p.dst0);
+      int ld = p.ldc0;
+      int colbase = n0;
+      if (p.shuffle) {
+        const int qd = n0 / p.cout_q;
+        colbase = n0 - qd * p.cout_q;
+        pix = (static_cast<long long>(pn) * (2 * p.g.H) + 2 * ph_ + (qd >> 1)) * (2 * p.g.W) + 2 * pw + (qd & 1);
+      } else if (p.split_c > 0 && n0 >= p.split_c) {
+        dst = reinterpret_cast<OutT*>(p.dst1);
+        ld = p.ldc1;
+        colbase = n0 - p.split_c;
+      }
+      OutT* drow = dst + (valid ? pix : 0) * ld + colbase;
+
+      mbar_wait(&acc_full[acc], pacc);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + chunk * 32, v);
+        tmem_ld_wait();
+        float f[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            f[2 * j] = valid ? bf16lo_to_f32(pk[j]) : 0.f;
-            f[2 * j + 1] = valid ? bf16hi_to_f32(pk[j]) : 0.f;
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(v[j]) + s_bias[chunk * 32 + j];
+          if (p.relu) x = fmaxf(x, 0.f);
+          f[j] = x;
+        }
+        if constexpr (sizeof(OutT) == 2) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+          if (valid && (n0 + chunk * 32) < p.n_store) {
+            uint4* o = reinterpret_cast<uint4*>(drow + chunk * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          }
+          if (do_stats) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              f[2 * j] = valid ? bf16lo_to_f32(pk[j]) : 0.f;
+              f[2 * j + 1] = valid ? bf16hi_to_f32(pk[j]) : 0.f;
+            }
+          }
+        } else {
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + chunk * 32 + j < p.n_store) drow[chunk * 32 + j] = f[j];
+          }
+          if (do_stats) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = valid ? f[j] : 0.f;
           }
         }
-      } else {
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + chunk * 32 + j < p.n_store) drow[chunk * 32 + j] = f[j];
-        }
         if (do_stats) {
+          // 32x32 transpose through shared memory: lane j then owns column (chunk*32 + j)
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = valid ? f[j] : 0.f;
+          for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = f[j];
+          __syncwarp();
+          float s = 0.f, sq = 0.f;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = scratch[i * 33 + lane];
+            s += x;
+            sq = fmaf(x, x, sq);
+          }
+          atomicAdd(&s_sum[chunk * 32 + lane], s);
+          atomicAdd(&s_sq[chunk * 32 + lane], sq);
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (do_stats) {
-        // 32x32 transpose through shared memory: lane j then owns column (chunk*32 + j)
-        __syncwarp();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = f[j];
-        __syncwarp();
-        float s = 0.f, sq = 0.f;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float x = scratch[i * 33 + lane];
-          s += x;
-          sq = fmaf(x, x, sq);
+        named_bar_sync(1, kEpiThreads);
+        for (int i = etid; i < BN; i += kEpiThreads) {
+          if (n0 + i < p.n_store) {
+            atomicAdd(&p.stat_sum[n0 + i], static_cast<double>(s_sum[i]));
+            atomicAdd(&p.stat_sq[n0 + i], static_cast<double>(s_sq[i]));
+          }
+          s_sum[i] = 0.f;
+          s_sq[i] = 0.f;
         }
-        atomicAdd(&s_sum[chunk * 32 + lane], s);
-        atomicAdd(&s_sq[chunk * 32 + lane], sq);
-      }
-    }
-    if (do_stats) {
-      named_bar_sync(1, kEpiThreads);
-      for (int i = threadIdx.x - 64; i < BN; i += kEpiThreads) {
-        if (n0 + i < p.n_store) {
-          atomicAdd(&p.stat_sum[n0 + i], static_cast<double>(s_sum[i]));
-          atomicAdd(&p.stat_sq[n0 + i], static_cast<double>(s_sq[i]));
-        }
+        named_bar_sync(1, kEpiThreads);
       }
     }
   }
@@ -845,7 +887,7 @@ cudaError_t launch_conv3(int BN, const CUtensorMap& a0, const CUtensorMap& a1, c
 // host side
 template <int BN, int STAGES>
 static constexpr int fprop_smem_bytes() {
-  return STAGES * (128 * 128 + BN * 128) + (2 * STAGES + 1) * 8 + 16 + 3 * BN * 4 + 1024;
+  return STAGES * (128 * 128 + BN * 128) + kFpScratch + 3 * BN * 4 + (2 * STAGES + 4) * 8 + 16 + 1024;
 }
 
 template <int BN, int STAGES, typename OutT>
@@ -860,8 +902,10 @@ static cudaError_t launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1,
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  igemm_fprop_kernel<BN, STAGES, OutT>
-      <<<dim3(m_tiles, n_tiles), kThreads, smem, st>>>(a0, a1, b, p);
+  int grid = m_tiles * n_tiles;
+  const int cap = g_fprop_sms * (smem <= 113 * 1024 ? 2 : 1);  // resident CTAs per SM by shared memory
+  if (grid > cap) grid = cap;
+  igemm_fprop_kernel<BN, STAGES, OutT><<<grid, kThreads, smem, st>>>(a0, a1, b, p, m_tiles, n_tiles);
   return cudaGetLastError();
 }
 
@@ -873,7 +917,7 @@ cudaError_t launch_fprop(int BN, int out_is_f32, const CUtensorMap& a0, const CU
     return cudaErrorInvalidValue;
   }
   switch (BN) {
-    case 64: return launch_fprop_t<64, 4, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
+    case 64: return launch_fprop_t<64, 3, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
     case 128: return launch_fprop_t<128, 3, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
     case 256: return launch_fprop_t<256, 4, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
     default: return cudaErrorInvalidValue;

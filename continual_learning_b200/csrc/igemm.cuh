@@ -63,6 +63,8 @@ struct WgradParams {
   int ld_u, ld_t;
 };
 
+void igemm_set_num_sms(int n);
+
 // Launchers (igemm.cu). Return cudaError_t from the launch; maps are built by the caller.
 cudaError_t launch_fprop(int BN, int out_is_f32, const CUtensorMap& a0, const CUtensorMap& a1,
                          const CUtensorMap& b, const FpropParams& p, int m_tiles, int n_tiles,

@@ -954,4 +954,117 @@ cudaError_t adam_multi_tensor(const AdamTensor* tensors, const void* blocks, int
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// table-driven batched variants: ONE launch packs / unpacks / converts every layer of the model
+// (per-layer launches of these tiny kernels cost more in launch latency than in bandwidth).
+// A job table is a device array of int64[16] rows; one thread block = one 32x32(xT) tile of one job.
+__device__ __forceinline__ int find_job(const long long* __restrict__ jobs, int njobs, int tile, int tile_col) {
+  int j = 0;
+  while (j + 1 < njobs && jobs[(j + 1) * 16 + tile_col] <= tile) ++j;
+  return j;
+}
+
+// row: {src, outAB, outBA, A, B, T, ldA, ldB, ldB2, ldA2, rev, tile0, tiles_b, -, -, -}
+__global__ void __launch_bounds__(256) pack_w_multi_kernel(const long long* __restrict__ jobs, int njobs) {
+  extern __shared__ float tile[];  // [32][32*T + 1]
+  const int j = find_job(jobs, njobs, blockIdx.x, 11);
+  const long long* J = jobs + j * 16;
+  const float* __restrict__ src = reinterpret_cast<const float*>(J[0]);
+  __nv_bfloat16* __restrict__ outAB = reinterpret_cast<__nv_bfloat16*>(J[1]);
+  __nv_bfloat16* __restrict__ outBA = reinterpret_cast<__nv_bfloat16*>(J[2]);
+  const int A = static_cast<int>(J[3]), B = static_cast<int>(J[4]), T = static_cast<int>(J[5]);
+  const int ldA = static_cast<int>(J[6]), ldB = static_cast<int>(J[7]);
+  const int ldB2 = static_cast<int>(J[8]), ldA2 = static_cast<int>(J[9]), rev = static_cast<int>(J[10]);
+  const int local = blockIdx.x - static_cast<int>(J[11]);
+  const int tiles_b = static_cast<int>(J[12]);
+  const int a0 = (local / tiles_b) * 32, b0 = (local % tiles_b) * 32;
+  const int na = min(32, A - a0), nb = min(32, B - b0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pitch = 32 * T + 1;
+  for (int ar = warp; ar < na; ar += 8) {
+    const float* row = src + (static_cast<long long>(a0 + ar) * B + b0) * T;
+    for (int rem = lane; rem < nb * T; rem += 32) tile[ar * pitch + rem] = row[rem];
+  }
+  __syncthreads();
+  if (outAB != nullptr) {
+    for (int t = 0; t < T; ++t)
+      for (int ar = warp; ar < na; ar += 8)
+        if (lane < nb)
+          outAB[(static_cast<long long>(t) * ldA + a0 + ar) * ldB + b0 + lane] =
+              __float2bfloat16_rn(tile[ar * pitch + lane * T + t]);
+  }
+  if (outBA != nullptr) {
+    for (int t = 0; t < T; ++t) {
+      const int tt = rev ? T - 1 - t : t;
+      for (int br = warp; br < nb; br += 8)
+        if (lane < na)
+          outBA[(static_cast<long long>(tt) * ldB2 + b0 + br) * ldA2 + a0 + lane] =
+              __float2bfloat16_rn(tile[lane * pitch + br * T + t]);
+    }
+  }
+}
+cudaError_t pack_w_multi(const void* jobs, int njobs, int total_tiles, int max_T, cudaStream_t st) {
+  if (total_tiles <= 0) return cudaSuccess;
+  const size_t smem = static_cast<size_t>(32) * (32 * max_T + 1) * sizeof(float);
+  pack_w_multi_kernel<<<total_tiles, 256, smem, st>>>(static_cast<const long long*>(jobs), njobs);
+  return cudaGetLastError();
+}
+
+// row: {D, grad, A, B, T, ldA, ldB, alpha (double bits), accumulate, tile0, tiles_b, ...}
+__global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const long long* __restrict__ jobs, int njobs) {
+  extern __shared__ float tile[];
+  const int j = find_job(jobs, njobs, blockIdx.x, 9);
+  const long long* J = jobs + j * 16;
+  const float* __restrict__ D = reinterpret_cast<const float*>(J[0]);
+  float* __restrict__ grad = reinterpret_cast<float*>(J[1]);
+  const int A = static_cast<int>(J[2]), B = static_cast<int>(J[3]), T = static_cast<int>(J[4]);
+  const int ldA = static_cast<int>(J[5]), ldB = static_cast<int>(J[6]);
+  const float alpha = static_cast<float>(__longlong_as_double(J[7]));
+  const int accumulate = static_cast<int>(J[8]);
+  const int local = blockIdx.x - static_cast<int>(J[9]);
+  const int tiles_b = static_cast<int>(J[10]);
+  const int a0 = (local / tiles_b) * 32, b0 = (local % tiles_b) * 32;
+  const int na = min(32, A - a0), nb = min(32, B - b0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pitch = 32 * T + 1;
+  for (int t = 0; t < T; ++t)
+    for (int ar = warp; ar < na; ar += 8)
+      if (lane < nb) tile[ar * pitch + lane * T + t] = D[(static_cast<long long>(t) * ldA + a0 + ar) * ldB + b0 + lane];
+  __syncthreads();
+  for (int ar = warp; ar < na; ar += 8) {
+    float* row = grad + (static_cast<long long>(a0 + ar) * B + b0) * T;
+    for (int rem = lane; rem < nb * T; rem += 32) {
+      const float v = alpha * tile[ar * pitch + rem];
+      row[rem] = accumulate ? row[rem] + v : v;
+    }
+  }
+}
+cudaError_t unpack_wgrad_multi(const void* jobs, int njobs, int total_tiles, int max_T, cudaStream_t st) {
+  if (total_tiles <= 0) return cudaSuccess;
+  const size_t smem = static_cast<size_t>(32) * (32 * max_T + 1) * sizeof(float);
+  unpack_wgrad_multi_kernel<<<total_tiles, 256, smem, st>>>(static_cast<const long long*>(jobs), njobs);
+  return cudaGetLastError();
+}
+
+// row: {src f64, dst f32, n, ld_group, groups, alpha (double bits), accumulate}; one block per job
+__global__ void f64_to_f32_multi_kernel(const long long* __restrict__ jobs) {
+  const long long* J = jobs + blockIdx.x * 16;
+  const double* __restrict__ src = reinterpret_cast<const double*>(J[0]);
+  float* __restrict__ dst = reinterpret_cast<float*>(J[1]);
+  const int n = static_cast<int>(J[2]), ld = static_cast<int>(J[3]), groups = static_cast<int>(J[4]);
+  const float alpha = static_cast<float>(__longlong_as_double(J[5]));
+  const int accumulate = static_cast<int>(J[6]);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double s = 0.0;
+    for (int g = 0; g < groups; ++g) s += src[g * ld + i];
+    const float v = alpha * static_cast<float>(s);
+    dst[i] = accumulate ? dst[i] + v : v;
+  }
+}
+cudaError_t f64_to_f32_multi(const void* jobs, int njobs, cudaStream_t st) {
+  if (njobs <= 0) return cudaSuccess;
+  f64_to_f32_multi_kernel<<<njobs, 256, 0, st>>>(static_cast<const long long*>(jobs));
+  return cudaGetLastError();
+}
+
 }  // namespace clk

@@ -56,5 +56,8 @@ cudaError_t argmax_confusion(const float* logits, const long long* labels, long 
 cudaError_t adam_multi_tensor(const AdamTensor* tensors, const void* blocks, int nblocks, int chunk,
                               float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
                               float gscale, const float* hyper, cudaStream_t st);
+cudaError_t pack_w_multi(const void* jobs, int njobs, int total_tiles, int max_T, cudaStream_t st);
+cudaError_t unpack_wgrad_multi(const void* jobs, int njobs, int total_tiles, int max_T, cudaStream_t st);
+cudaError_t f64_to_f32_multi(const void* jobs, int njobs, cudaStream_t st);
 
 }  // namespace clk

@@ -53,6 +53,7 @@ class UNetEngine:
         self.head = m.last[6]
         self._dev = None
         self._wver = None
+        self._job_ptrs = None
         self.training_fwd = True
         self.logits = None
 
@@ -119,20 +120,83 @@ class UNetEngine:
             ob += co
         self.hdbias = self.acc_b[ob:ob + 64]
         self._wver = None
+        self._job_ptrs = None
 
     def _pack_weights(self):
         ver = (_lib.param_epoch,) + tuple(p._version for p in self.params) + tuple(p.data_ptr() for p in self.params[:2])
         if ver == self._wver:
             return
-        for u in self.units:
-            if u.stem:
-                ops.pack_stem(u.conv.weight.detach(), u.wf)
-            else:
-                ops.pack_conv3x3(u.conv.weight.detach(), u.wf, u.wd)
-        for j, (mod, _, _) in enumerate(self.convT):
-            ops.pack_convT(mod.weight.detach(), self.twf[j], self.twd[j])
-        ops.pack_head(self.head.weight.detach(), self.hwf, self.hwd)
+        ptrs = tuple(p.data_ptr() for p in self.params)
+        if ptrs != self._job_ptrs:
+            self._build_jobs()
+            self._job_ptrs = ptrs
+        _lib.call("clk_pack_w_multi", self.pack_jobs, self.pack_n, self.pack_tiles, 9)
         self._wver = ver
+
+    # ------------------------------------------------------------------ batched job tables
+    @staticmethod
+    def _tiles(a, b):
+        return ((a + 31) // 32) * ((b + 31) // 32), (b + 31) // 32
+
+    def _build_jobs(self):
+        """int64[16] rows for clk_pack_w_multi / clk_unpack_wgrad_multi / clk_f64_to_f32_multi (include/clk.h)."""
+        import struct
+        one = struct.unpack("q", struct.pack("d", 1.0))[0]
+        dev = self._dev
+        c = self.m.conv_dim
+        nc = self.m.num_classes
+        pack, t0 = [], 0
+        unpack = [[], []]   # group 0: head + decoder (final first in backward), group 1: encoder
+        cvt = [[], []]
+        ut0 = [0, 0]
+
+        def add_pack(src, ab, ba, A, B, T, ldA, ldB, ldB2, ldA2, rev):
+            nonlocal t0
+            n, tb = self._tiles(A, B)
+            pack.append([src.data_ptr(), ab.data_ptr() if ab is not None else 0, ba.data_ptr() if ba is not None else 0,
+                         A, B, T, ldA, ldB, ldB2, ldA2, rev, t0, tb, 0, 0, 0])
+            t0 += n
+
+        def add_unpack(g, D, grad, A, B, T, ldA, ldB):
+            n, tb = self._tiles(A, B)
+            unpack[g].append([D.data_ptr(), grad.data_ptr(), A, B, T, ldA, ldB, one, 0, ut0[g], tb, 0, 0, 0, 0, 0])
+            ut0[g] += n
+
+        def add_cvt(g, src, dst, n):
+            cvt[g].append([src.data_ptr(), dst.data_ptr(), n, 0, 1, one, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+
+        for i, u in enumerate(self.units):
+            g = 1 if i < 8 else 0
+            w = u.conv.weight
+            if u.stem:
+                k = self.m.in_dim * 9
+                add_pack(w, u.wf, None, u.cout, k, 1, u.cout, 64, 0, 0, 0)
+                add_unpack(g, u.gp, self.gview[w], u.cout, k, 1, 64, 64)
+            else:
+                ci = u.c0 + u.c1
+                add_pack(w, u.wf, u.wd, u.cout, ci, 9, u.cout, ci, ci, u.cout, 1)
+                add_unpack(g, u.gp, self.gview[w], u.cout, ci, 9, u.cout, ci)
+            add_cvt(g, u.dbias, self.gview[u.conv.bias], u.cout)
+        for j, (mod, cm, co) in enumerate(self.convT):
+            add_pack(mod.weight, self.twd[j], self.twf[j], cm, co, 4, cm, co, co, cm, 0)
+            add_unpack(0, self.tgp[j], self.gview[mod.weight], cm, co, 4, cm, co)
+            add_cvt(0, self.tdbias[j], self.gview[mod.bias], co)
+        add_pack(self.head.weight, self.hwf, self.hwd, nc, c, 1, 32, c, c, 64, 0)
+        add_unpack(0, self.hgp, self.gview[self.head.weight], nc, c, 1, 64, c)
+        add_cvt(0, self.hdbias, self.gview[self.head.bias], nc)
+
+        def dev_table(rows):
+            return torch.tensor(rows, dtype=torch.int64).to(dev)
+
+        self.pack_jobs, self.pack_n, self.pack_tiles = dev_table(pack), len(pack), t0
+        self.unpack_jobs = [(dev_table(unpack[g]), len(unpack[g]), ut0[g]) for g in range(2)]
+        self.cvt_jobs = [(dev_table(cvt[g]), len(cvt[g])) for g in range(2)]
+
+    def _flush_grads(self, g):
+        tab, n, tiles = self.unpack_jobs[g]
+        _lib.call("clk_unpack_wgrad_multi", tab, n, tiles, 9)
+        tab, n = self.cvt_jobs[g]
+        _lib.call("clk_f64_to_f32_multi", tab, n)
 
     # ------------------------------------------------------------------ forward
     def _unit_fwd(self, u, x0, x1, training, pool=False):
@@ -208,13 +272,10 @@ class UNetEngine:
         ops.bn_bwd_finalize(u.s1, u.s2, bn.weight.detach(), mean, invstd, self.gview[bn.weight], self.gview[bn.bias],
                             ka, kb, kc, n * h * w, training=self.training_fwd)
         dpre = ops.bn_relu_bwd_apply(dz, u.y, ka, kb, kc, u.dbias)
-        ops.f64_to_f32(u.dbias, self.gview[u.conv.bias])
         if u.stem:
             ops.gemm_wgrad(dpre, u.x0, out=u.gp)
-            ops.unpack_wgrad(u.gp, self.gview[u.conv.weight], u.cout, self.m.in_dim * 9, 1, 64, 64)
             return None, None
         ops.conv3x3_wgrad(dpre, u.x0, u.x1, out=u.gp)
-        ops.unpack_wgrad(u.gp, self.gview[u.conv.weight], u.cout, u.c0 + u.c1, 9, u.cout, u.c0 + u.c1)
         if not need_dx:
             return None, None
         return ops.conv3x3_dgrad(dpre, u.wd, u.c0, u.c1)
@@ -222,9 +283,7 @@ class UNetEngine:
     def _convT_bwd(self, j, dy):
         mod, cm, co = self.convT[j]
         ops.convT_wgrad(self.tin[j], dy, out=self.tgp[j])
-        ops.unpack_wgrad(self.tgp[j], self.gview[mod.weight], cm, co, 4, cm, co)
         ops.channel_sum(dy, self.tdbias[j])
-        ops.f64_to_f32(self.tdbias[j], self.gview[mod.bias])
         return ops.convT_dgrad(dy, self.twd[j])
 
     def backward(self, dlogits, after_decoder=None):
@@ -238,9 +297,7 @@ class UNetEngine:
         self.Gp.zero_()
         # 1x1 head (models/unet.py:72)
         ops.gemm_wgrad(dlogits, U[17].z, out=self.hgp)
-        ops.unpack_wgrad(self.hgp, self.gview[self.head.weight], nc, self.m.conv_dim, 1, 64, self.m.conv_dim)
         ops.channel_sum(dlogits, self.hdbias)
-        ops.f64_to_f32(self.hdbias, self.gview[self.head.bias], n=nc)
         dz = ops.gemm_fprop(dlogits, self.hwd, None, self.m.conv_dim)
         dz, _ = self._unit_bwd(U[17], dz)
         skip_grads = []
@@ -255,6 +312,7 @@ class UNetEngine:
                 skip_grads.append(dskip)  # enc2, enc3, enc4 in that order
             else:
                 dpool = dskip  # gradient of the centre pool output
+        self._flush_grads(0)  # head + decoder gradients -> PyTorch layout (one batched launch each)
         if after_decoder is not None:
             after_decoder()
         # encoder, deepest first: enc4 (U[7]) .. enc1 (U[1])
@@ -262,6 +320,7 @@ class UNetEngine:
             dz = ops.maxpool_bwd_add(dpool, U[k].idx, skip_grads[lvl])
             dz, _ = self._unit_bwd(U[k], dz)
             dpool, _ = self._unit_bwd(U[k - 1], dz, need_dx=(k > 1))
+        self._flush_grads(1)  # encoder gradients
         return [self.gview[p] for p in self.params]
 
     def release(self):

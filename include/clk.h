@@ -57,6 +57,16 @@ int clk_pack_w(const float* src, void* outAB, void* outBA, int A, int B, int T, 
 int clk_unpack_wgrad(const float* D, float* grad, int A, int B, int T, int ldA, int ldB, float alpha,
                      int accumulate, clk_stream_t st);
 
+/* Batched (table-driven) forms: ONE launch for every layer of the model. `jobs` is a device array of
+ * int64[16] rows (pointers and ints widened to int64, alpha as the bit pattern of a double):
+ *   pack:    {src, outAB, outBA, A, B, T, ldA, ldB, ldB2, ldA2, rev, tile0, tiles_b}
+ *   unpack:  {D, grad, A, B, T, ldA, ldB, alpha, accumulate, tile0, tiles_b}
+ *   convert: {src_f64, dst_f32, n, ld_group, groups, alpha, accumulate}   (one block per row)
+ * tile0 = index of the job's first 32x32 tile in the launch grid, tiles_b = ceil(B/32). */
+int clk_pack_w_multi(const void* jobs, int njobs, int total_tiles, int max_T, clk_stream_t st);
+int clk_unpack_wgrad_multi(const void* jobs, int njobs, int total_tiles, int max_T, clk_stream_t st);
+int clk_f64_to_f32_multi(const void* jobs, int njobs, clk_stream_t st);
+
 /* ---- tcgen05 implicit GEMMs ----
  * conv3x3, stride 1, zero pad 1 (nn.Conv2d at models/unet.py:13,16,28,31,53,66,69) fused with
  * bias + ReLU (models/unet.py:14,17,...) and the per-channel sum / sum-of-squares BatchNorm needs.
