@@ -1,0 +1,128 @@
+"""Launch a fixed list of representative kernels at the benchmark shapes (each twice: warm-up + profiled) so that
+`ncu --set full -k regex:... ` can capture them in one short run.  Developer tool (run under gpurun).
+
+    python scripts/dev_ncu_targets.py [names...]     # default: all
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch
+
+from continual_learning_b200 import _lib, ops
+
+bf16 = torch.bfloat16
+dev = "cuda"
+B, S = 16, 256
+
+
+def t(*shape):
+    return torch.randn(*shape, device=dev).to(bf16)
+
+
+def conv_case(c0, c1, co, d):
+    h = w = S // d
+    x0, x1 = t(B, h, w, c0), (t(B, h, w, c1) if c1 else None)
+    wt = torch.randn(co, c0 + c1, 3, 3, device=dev) * 0.05
+    wf, wd = ops.pack_conv3x3(wt)
+    dy = t(B, h, w, co)
+    return x0, x1, wf, wd, dy, torch.zeros(co, device=dev), h, w
+
+
+def main():
+    _lib.ensure_device(0)
+    want = set(sys.argv[1:])
+    cases = {}
+
+    def case(name):
+        def deco(fn):
+            cases[name] = fn
+            return fn
+        return deco
+
+    @case("fprop64")
+    def _():
+        x0, x1, wf, wd, dy, b, h, w = conv_case(64, 0, 64, 1)
+        ss = torch.zeros(64, device=dev, dtype=torch.float64)
+        return lambda: ops.conv3x3_fprop(x0, x1, wf, b, relu=True, stats=(ss, ss.clone()))
+
+    @case("fprop128")
+    def _():
+        x0, x1, wf, wd, dy, b, h, w = conv_case(128, 0, 128, 2)
+        ss = torch.zeros(128, device=dev, dtype=torch.float64)
+        return lambda: ops.conv3x3_fprop(x0, x1, wf, b, relu=True, stats=(ss, ss.clone()))
+
+    @case("dgrad64")
+    def _():
+        x0, x1, wf, wd, dy, b, h, w = conv_case(64, 0, 64, 1)
+        return lambda: ops.conv3x3_dgrad(dy, wd, 64, 0)
+
+    @case("wgrad64")
+    def _():
+        x0, x1, wf, wd, dy, b, h, w = conv_case(64, 0, 64, 1)
+        dw = torch.zeros(9, 64, 64, device=dev)
+        return lambda: ops.conv3x3_wgrad(dy, x0, None, out=dw)
+
+    @case("wgrad512")
+    def _():
+        x0, x1, wf, wd, dy, b, h, w = conv_case(512, 0, 512, 8)
+        dw = torch.zeros(9, 512, 512, device=dev)
+        return lambda: ops.conv3x3_wgrad(dy, x0, None, out=dw)
+
+    @case("stem")
+    def _():
+        a = t(B, S, S, 64)
+        wf = t(64, 64)
+        ss = torch.zeros(64, device=dev, dtype=torch.float64)
+        b = torch.zeros(64, device=dev)
+        return lambda: ops.gemm_fprop(a, wf, b, 64, relu=True, stats=(ss, ss.clone()))
+
+    @case("head")
+    def _():
+        a = t(B, S, S, 64)
+        wf = t(32, 64)
+        b = torch.zeros(21, device=dev)
+        return lambda: ops.gemm_fprop(a, wf, b, 21, out_f32=True)
+
+    @case("convT_wgrad")
+    def _():
+        x = t(B, S // 2, S // 2, 128)
+        dy = t(B, S, S, 64)
+        dw = torch.zeros(4, 128, 64, device=dev)
+        return lambda: ops.convT_wgrad(x, dy, out=dw)
+
+    @case("convT_fprop")
+    def _():
+        x = t(B, S // 2, S // 2, 128)
+        wf = t(256, 128)
+        b = torch.zeros(64, device=dev)
+        return lambda: ops.convT_fprop(x, wf, b)
+
+    @case("bn_bwd")
+    def _():
+        y, dz = t(B, S, S, 64), t(B, S, S, 64)
+        k = torch.ones(64, device=dev)
+        db = torch.zeros(64, device=dev, dtype=torch.float64)
+        out = torch.empty_like(y)
+        return lambda: ops.bn_relu_bwd_apply(dz, y, k, k, k, db, out=out)
+
+    @case("bn_reduce")
+    def _():
+        y, dz = t(B, S, S, 64), t(B, S, S, 64)
+        s1 = torch.zeros(64, device=dev, dtype=torch.float64)
+        return lambda: ops.bn_bwd_reduce(dz, y, s1, s1.clone())
+
+    for name, make in cases.items():
+        if want and name not in want:
+            continue
+        fn = make()
+        fn()
+        torch.cuda.synchronize()
+        fn()
+        torch.cuda.synchronize()
+        print("ran", name, flush=True)
+
+
+if __name__ == "__main__":
+    main()
