@@ -31,7 +31,7 @@ SIGNATURES = {
     "clk_nhwc_to_nchw_f32": [p, i, p, i, i, i, i, i, p],
     "clk_im2col3x3_stem": [p, p, i, i, i, i, p],
     "clk_pack_w": [p, p, p, i, i, i, i, i, i, i, i, p],
-    "clk_unpack_wgrad": [p, p, i, i, i, i, i, f, i, p],
+    "clk_unpack_wgrad": [p, p, i, i, i, i, i, f, i, i, p],
     "clk_pack_w_multi": [p, i, i, i, p],
     "clk_unpack_wgrad_multi": [p, i, i, i, p],
     "clk_f64_to_f32_multi": [p, i, p],

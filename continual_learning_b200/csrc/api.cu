@@ -253,9 +253,9 @@ int clk_pack_w(const float* src, void* outAB, void* outBA, int A, int B, int T, 
   return cuda_status(pack_w(src, outAB, outBA, A, B, T, ldA, ldB, ldB2, ldA2, rev, S(st)), "pack_w");
 }
 int clk_unpack_wgrad(const float* D, float* grad, int A, int B, int T, int ldA, int ldB, float alpha,
-                     int accumulate, clk_stream_t st) {
+                     int accumulate, int transposed, clk_stream_t st) {
   if (!D || !grad || A <= 0 || B <= 0 || T <= 0 || T > 9) return fail(CLK_E_BADARG, "unpack_wgrad: bad args");
-  return cuda_status(unpack_wgrad(D, grad, A, B, T, ldA, ldB, alpha, accumulate, S(st)), "unpack_wgrad");
+  return cuda_status(unpack_wgrad(D, grad, A, B, T, ldA, ldB, alpha, accumulate, transposed, S(st)), "unpack_wgrad");
 }
 
 int clk_pack_w_multi(const void* jobs, int njobs, int total_tiles, int max_T, clk_stream_t st) {
@@ -431,6 +431,7 @@ int clk_conv3x3_wgrad(const void* dy, int Cout, const void* x0, int C0, const vo
   p.out = dw;
   p.ld_u = Cout;
   p.ld_t = Cin;
+  p.transpose_out = 1;  // same packed layout as the halo kernel: [9][Cin][Cout]
   CUtensorMap u, t0, t1;
   CHECK_RC(map_nhwc(&u, dy, N, H, W, Cout, p.g.tw, p.g.th, p.g.nb));
   CHECK_RC(map_nhwc(&t0, x0, N, H, W, C0, p.g.tw, p.g.th, p.g.nb));

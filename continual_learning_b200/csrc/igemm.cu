@@ -81,10 +81,12 @@ __device__ __forceinline__ uint8_t* align1024(uint8_t* raw) {
 // across tiles and two TMEM accumulator stages let the epilogue of tile i overlap the main loop of tile i+1.
 // Used for the 1-tap GEMMs (stem, 1x1 head, head dgrad, ConvTranspose2d forward), the 4-tap ConvTranspose2d
 // dgrad and the conv3x3 layers on small feature maps (BN = 256).
-constexpr int kFpScratch = 4 * 32 * 33 * 4;
+constexpr int kFpScratch = 8 * 32 * 33 * 4;
+constexpr int kFpThreads = 64 + 256;  // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
+constexpr int kFpEpiThreads = 256;
 
 template <int BN, int STAGES, typename OutT>
-__global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
+__global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
     igemm_fprop_kernel(const __grid_constant__ CUtensorMap mapA0,
                        const __grid_constant__ CUtensorMap mapA1,
                        const __grid_constant__ CUtensorMap mapB,
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   float* scratch_all = reinterpret_cast<float*>(sB + STAGES * B_BYTES);
-  float* s_bias = scratch_all + 4 * 32 * 33;
+  float* s_bias = scratch_all + 8 * 32 * 33;
   float* s_sum = s_bias + BN;
   float* s_sq = s_sum + BN;
   uint64_t* full = reinterpret_cast<uint64_t*>(s_sq + BN);
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], 8);
     }
     fence_mbar_init();
     tma_prefetch_desc(&mapA0);
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < 3 * BN; i += kThreads) s_bias[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * BN; i += kFpThreads) s_bias[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
   } else {
     // ------------------------------------------------ epilogue: TMEM -> regs -> global
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;  // the two warps of a quadrant split the 32-column chunks
     const int m = q * 32 + lane;
     const int etid = threadIdx.x - 64;
     const bool do_stats = p.stat_sum != nullptr;
@@ -203,8 +206,8 @@ __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
       const int n0 = nt * BN;
       const uint32_t acc = itile & 1, pacc = (itile >> 1) & 1;
       if (nt != bias_nt) {
-        named_bar_sync(2, kEpiThreads);
-        for (int i = etid; i < BN; i += kEpiThreads) {
+        named_bar_sync(2, kFpEpiThreads);
+        for (int i = etid; i < BN; i += kFpEpiThreads) {
           float bv = 0.f;
           if (p.bias != nullptr) {
             const int col = n0 + i;
@@ -213,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
           }
           s_bias[i] = bv;
         }
-        named_bar_sync(2, kEpiThreads);
+        named_bar_sync(2, kFpEpiThreads);
         bias_nt = nt;
       }
       int b1, b2, b3, b4;
@@ -238,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
       mbar_wait(&acc_full[acc], pacc);
       tc_fence_after();
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int chunk = half; chunk < BN / 32; chunk += 2) {
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_COLS + chunk * 32, v);
         tmem_ld_wait();
@@ -298,8 +301,8 @@ __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (do_stats) {
-        named_bar_sync(1, kEpiThreads);
-        for (int i = etid; i < BN; i += kEpiThreads) {
+        named_bar_sync(1, kFpEpiThreads);
+        for (int i = etid; i < BN; i += kFpEpiThreads) {
           if (n0 + i < p.n_store) {
             atomicAdd(&p.stat_sum[n0 + i], static_cast<double>(s_sum[i]));
             atomicAdd(&p.stat_sq[n0 + i], static_cast<double>(s_sq[i]));
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 128 ? 2 : 1))
           s_sum[i] = 0.f;
           s_sq[i] = 0.f;
         }
-        named_bar_sync(1, kEpiThreads);
+        named_bar_sync(1, kFpEpiThreads);
       }
     }
   }
@@ -447,15 +450,27 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc_fence_after();
     for (int g = 0; g < gcount; ++g) {
       float* orow = p.out + (static_cast<size_t>(tap0 + g) * p.ld_u + (valid ? u : 0)) * p.ld_t + ct0;
+      // transposed: out[tap][t][u] (the conv3x3 layout [tap][Cin][Cout]); lanes = consecutive u -> coalesced
+      float* ocol = p.out + (static_cast<size_t>(tap0 + g) * p.ld_t + ct0) * p.ld_u + (valid ? u : 0);
 #pragma unroll 1
       for (int chunk = 0; chunk < BN / 32; ++chunk) {
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * BN + chunk * 32, v);
         tmem_ld_wait();
         if (valid) {
+          if (p.transpose_out) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (ct0 + chunk * 32 + j < p.CT) atomicAdd(orow + chunk * 32 + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j) {
+              if (ct0 + chunk * 32 + j < p.CT)
+                atomicAdd(ocol + static_cast<size_t>(chunk * 32 + j) * p.ld_u, __uint_as_float(v[j]));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              if (ct0 + chunk * 32 + 4 * j + 3 < p.CT)
+                red_add_v4(orow + chunk * 32 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                           __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
           }
         }
       }
@@ -573,7 +588,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc_fence_after();
     for (int pr = 0; pr < 5; ++pr) {
       const int tap = 2 * pr + (row >> 6);
-      float* obase = p.out + (static_cast<size_t>(tap) * p.Cout + co_tile * 64) * p.Cin + ci;
+      // packed gradient layout [tap][Cin][Cout]: this thread owns one (tap, ci) row -> 32 consecutive floats per chunk
+      float* obase = p.out + (static_cast<size_t>(tap) * p.Cin + ci) * p.Cout + co_tile * 64;
 #pragma unroll 1
       for (int chunk = 0; chunk < 2; ++chunk) {
         uint32_t v[32];
@@ -581,8 +597,9 @@ __global__ void __launch_bounds__(kThreads, 1)
         tmem_ld_wait();
         if (tap < 9) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            atomicAdd(obase + static_cast<size_t>(chunk * 32 + j) * p.Cin, __uint_as_float(v[j]));
+          for (int j = 0; j < 8; ++j)
+            red_add_v4(obase + chunk * 32 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         }
       }
     }
@@ -905,7 +922,7 @@ static cudaError_t launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1,
   int grid = m_tiles * n_tiles;
   const int cap = g_fprop_sms * (smem <= 113 * 1024 ? 2 : 1);  // resident CTAs per SM by shared memory
   if (grid > cap) grid = cap;
-  igemm_fprop_kernel<BN, STAGES, OutT><<<grid, kThreads, smem, st>>>(a0, a1, b, p, m_tiles, n_tiles);
+  igemm_fprop_kernel<BN, STAGES, OutT><<<grid, kFpThreads, smem, st>>>(a0, a1, b, p, m_tiles, n_tiles);
   return cudaGetLastError();
 }
 
@@ -919,7 +936,7 @@ cudaError_t launch_fprop(int BN, int out_is_f32, const CUtensorMap& a0, const CU
   switch (BN) {
     case 64: return launch_fprop_t<64, 3, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
     case 128: return launch_fprop_t<128, 3, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
-    case 256: return launch_fprop_t<256, 4, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
+    case 256: return launch_fprop_t<256, 3, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -59,8 +59,9 @@ struct WgradParams {
   int ct_split;        // channels that live in T source 0
   int m_tiles, n_tiles, tap_groups;
   int ksplit, tiles_total;
-  float* out;          // [ntaps][ld_u][ld_t] fp32, accumulated with red.add (caller zeroes)
+  float* out;          // [ntaps][ld_u][ld_t] fp32 (or [ntaps][ld_t][ld_u] when transpose_out), red.add accumulated
   int ld_u, ld_t;
+  int transpose_out;
 };
 
 void igemm_set_num_sms(int n);
@@ -83,7 +84,7 @@ struct Wgrad9Params {
   int cout_tiles;                     // 64-channel tiles of dY
   int ksplit;
   int Cin, Cout;
-  float* out;                         // [9][Cout][Cin] fp32, red.add accumulated (caller zeroes)
+  float* out;                         // [9][Cin][Cout] fp32, red.add accumulated (caller zeroes)
 };
 cudaError_t launch_wgrad9(const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
                           const Wgrad9Params& p, cudaStream_t st);

@@ -242,15 +242,21 @@ cudaError_t pack_w(const float* src, void* outAB, void* outBA, int A, int B, int
 
 // packed fp32 gradient D[T][ldA][ldB] -> grad[A][B][T] (dst = alpha*D, or dst += alpha*D)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ D, float* __restrict__ grad, int A, int B,
-                                    int T, int ldA, int ldB, float alpha, int accumulate) {
+                                    int T, int ldA, int ldB, float alpha, int accumulate, int transposed) {
   extern __shared__ float tile[];  // [32 a][32*T + 1]
   const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
   const int pitch = 32 * T + 1;
   for (int idx = threadIdx.x; idx < T * 1024; idx += blockDim.x) {
     const int t = idx / 1024, r = (idx / 32) % 32, c = idx % 32;
-    float v = 0.f;
-    if (a0 + r < A && b0 + c < B) v = D[(static_cast<long long>(t) * ldA + a0 + r) * ldB + b0 + c];
-    tile[r * pitch + c * T + t] = v;
+    if (transposed) {  // D is [T][ldB][ldA]: r walks b, c walks a
+      float v = 0.f;
+      if (a0 + c < A && b0 + r < B) v = D[(static_cast<long long>(t) * ldB + b0 + r) * ldA + a0 + c];
+      tile[c * pitch + r * T + t] = v;
+    } else {
+      float v = 0.f;
+      if (a0 + r < A && b0 + c < B) v = D[(static_cast<long long>(t) * ldA + a0 + r) * ldB + b0 + c];
+      tile[r * pitch + c * T + t] = v;
+    }
   }
   __syncthreads();
   const int rowlen = 32 * T;
@@ -265,10 +271,10 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ D, float* __restri
   }
 }
 cudaError_t unpack_wgrad(const float* D, float* grad, int A, int B, int T, int ldA, int ldB, float alpha,
-                         int accumulate, cudaStream_t st) {
+                         int accumulate, int transposed, cudaStream_t st) {
   dim3 grid((B + 31) / 32, (A + 31) / 32);
   const size_t smem = static_cast<size_t>(32) * (32 * T + 1) * sizeof(float);
-  unpack_wgrad_kernel<<<grid, 256, smem, st>>>(D, grad, A, B, T, ldA, ldB, alpha, accumulate);
+  unpack_wgrad_kernel<<<grid, 256, smem, st>>>(D, grad, A, B, T, ldA, ldB, alpha, accumulate, transposed);
   return cudaGetLastError();
 }
 
@@ -314,32 +320,47 @@ cudaError_t bn_finalize(const double* sum, const double* sq, const float* gamma,
   return cudaGetLastError();
 }
 
-// z = scale[c]*y + shift[c]   (NHWC bf16, C % 8 == 0)
-__global__ void bn_apply_kernel(const uint4* __restrict__ y, uint4* __restrict__ z,
-                                const float* __restrict__ scale, const float* __restrict__ shift,
-                                long long nvec, int CV) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % CV);
+// z = scale[c]*y + shift[c]   (NHWC bf16, C % 8 == 0).  blockDim (256) is a multiple of CV, so the channel
+// column of a thread never changes: coefficients live in registers; two 16-byte loads in flight per thread.
+__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, uint4* __restrict__ z,
+                                                        const float* __restrict__ scale,
+                                                        const float* __restrict__ shift, long long nvec, int CV) {
+  const int cv = threadIdx.x % CV;
+  float a[8], c[8];
+  {
     const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale) + cv * 2);
     const float4 a1 = __ldg(reinterpret_cast<const float4*>(scale) + cv * 2 + 1);
     const float4 c0 = __ldg(reinterpret_cast<const float4*>(shift) + cv * 2);
     const float4 c1 = __ldg(reinterpret_cast<const float4*>(shift) + cv * 2 + 1);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+  }
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += 2 * stride) {
+    const bool two = i + stride < nvec;
+    const uint4 v0 = ldg_stream(y + i);
+    const uint4 v1 = two ? ldg_stream(y + i + stride) : make_uint4(0, 0, 0, 0);
     float f[8];
-    unpack8(ldg_stream(y + i), f);
-    f[0] = fmaf(f[0], a0.x, c0.x); f[1] = fmaf(f[1], a0.y, c0.y);
-    f[2] = fmaf(f[2], a0.z, c0.z); f[3] = fmaf(f[3], a0.w, c0.w);
-    f[4] = fmaf(f[4], a1.x, c1.x); f[5] = fmaf(f[5], a1.y, c1.y);
-    f[6] = fmaf(f[6], a1.z, c1.z); f[7] = fmaf(f[7], a1.w, c1.w);
+    unpack8(v0, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], a[e], c[e]);
     z[i] = pack8(f);
+    if (two) {
+      unpack8(v1, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], a[e], c[e]);
+      z[i + stride] = pack8(f);
+    }
   }
 }
 cudaError_t bn_apply(const void* y, void* z, const float* scale, const float* shift, long long P, int C,
                      cudaStream_t st) {
   const long long nvec = P * (C / 8);
-  bn_apply_kernel<<<grid_for(nvec, 256 * 4, 16), 256, 0, st>>>(static_cast<const uint4*>(y),
-                                                               static_cast<uint4*>(z), scale, shift, nvec,
-                                                               C / 8);
+  const int CV = C / 8;
+  if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
+  const int threads = (256 / CV) * CV;  // a multiple of CV: the channel column of a thread is then constant
+  bn_apply_kernel<<<grid_for(nvec, threads * 4, 8), threads, 0, st>>>(static_cast<const uint4*>(y),
+                                                                      static_cast<uint4*>(z), scale, shift, nvec, CV);
   return cudaGetLastError();
 }
 
@@ -515,20 +536,53 @@ cudaError_t bn_stats(const void* y, double* sum, double* sq, long long P, int C,
   return cudaGetLastError();
 }
 
-// S1 = sum dz, S2 = sum dz*y  (per channel)
-__global__ void bn_bwd_reduce_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ y,
-                                     double* __restrict__ s1, double* __restrict__ s2, long long P,
-                                     int CV) {
-  channel_reduce<2>(P, CV, s1, s2, [&](long long p, int cv, float* acc) {
+// S1 = sum dz, S2 = sum dz*y  (per channel).  Same thread mapping as channel_reduce, two pixel rows in flight.
+__global__ void __launch_bounds__(256, 4)
+    bn_bwd_reduce_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ y, double* __restrict__ s1,
+                         double* __restrict__ s2, long long P, int CV) {
+  extern __shared__ float red[];
+  const int rows = blockDim.x / CV;
+  const int cv = threadIdx.x % CV;
+  const int r = threadIdx.x / CV;
+  float acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * rows;
+  for (long long p = blockIdx.x * static_cast<long long>(rows) + r; r < rows && p < P; p += 2 * stride) {
+    const bool two = p + stride < P;
+    const uint4 g0 = ldg_stream(dz + p * CV + cv), f0 = ldg_stream(y + p * CV + cv);
+    uint4 g1 = make_uint4(0, 0, 0, 0), f1 = g1;
+    if (two) {
+      g1 = ldg_stream(dz + (p + stride) * CV + cv);
+      f1 = ldg_stream(y + (p + stride) * CV + cv);
+    }
     float g[8], f[8];
-    unpack8(ldg_stream(dz + p * CV + cv), g);
-    unpack8(ldg_stream(y + p * CV + cv), f);
+    unpack8(g0, g);
+    unpack8(f0, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       acc[e] += g[e];
       acc[8 + e] = fmaf(g[e], f[e], acc[8 + e]);
     }
-  });
+    unpack8(g1, g);
+    unpack8(f1, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[e] += g[e];
+      acc[8 + e] = fmaf(g[e], f[e], acc[8 + e]);
+    }
+  }
+  const int width = CV * 16;
+  if (r < rows) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) red[r * width + (e / 8) * CV * 8 + cv * 8 + (e % 8)] = acc[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < width; i += blockDim.x) {
+    float s = 0.f;
+    for (int rr = 0; rr < rows; ++rr) s += red[rr * width + i];
+    atomicAdd((i < CV * 8 ? s1 : s2) + (i % (CV * 8)), static_cast<double>(s));
+  }
 }
 cudaError_t bn_bwd_reduce(const void* dz, const void* y, double* s1, double* s2, long long P, int C,
                           cudaStream_t st) {
@@ -536,7 +590,7 @@ cudaError_t bn_bwd_reduce(const void* dz, const void* y, double* s1, double* s2,
   if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
   const int rows = 256 / CV;
   const size_t smem = static_cast<size_t>(rows) * CV * 16 * sizeof(float);
-  bn_bwd_reduce_kernel<<<grid_for(P, rows * 8, 8), 256, smem, st>>>(
+  bn_bwd_reduce_kernel<<<grid_for(P, rows * 8, 4), 256, smem, st>>>(
       static_cast<const uint4*>(dz), static_cast<const uint4*>(y), s1, s2, P, CV);
   return cudaGetLastError();
 }
@@ -578,24 +632,38 @@ cudaError_t bn_bwd_finalize(const double* s1, const double* s2, const float* gam
   return cudaGetLastError();
 }
 
-// dpre = (y > 0) ? kA*dz + kB*y + kC : 0 ; dbias[c] += sum dpre
-__global__ void bn_relu_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ y,
-                                         uint4* __restrict__ dpre, const float* __restrict__ kA,
-                                         const float* __restrict__ kB, const float* __restrict__ kC,
-                                         double* __restrict__ dbias, long long P, int CV) {
-  channel_reduce<1>(P, CV, dbias, dbias, [&](long long p, int cv, float* acc) {
+// dpre = (y > 0) ? kA*dz + kB*y + kC : 0 ; dbias[c] += sum dpre.  Coefficients hoisted, two rows in flight.
+__global__ void __launch_bounds__(256, 4)
+    bn_relu_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ y, uint4* __restrict__ dpre,
+                             const float* __restrict__ kA, const float* __restrict__ kB,
+                             const float* __restrict__ kC, double* __restrict__ dbias, long long P, int CV) {
+  extern __shared__ float red[];
+  const int rows = blockDim.x / CV;
+  const int cv = threadIdx.x % CV;
+  const int r = threadIdx.x / CV;
+  float ka[8], kb[8], kc[8], acc[8];
+  {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(kA) + cv * 2), a1 = __ldg(reinterpret_cast<const float4*>(kA) + cv * 2 + 1);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(kB) + cv * 2), b1 = __ldg(reinterpret_cast<const float4*>(kB) + cv * 2 + 1);
+    const float4 c0 = __ldg(reinterpret_cast<const float4*>(kC) + cv * 2), c1 = __ldg(reinterpret_cast<const float4*>(kC) + cv * 2 + 1);
+    ka[0] = a0.x; ka[1] = a0.y; ka[2] = a0.z; ka[3] = a0.w; ka[4] = a1.x; ka[5] = a1.y; ka[6] = a1.z; ka[7] = a1.w;
+    kb[0] = b0.x; kb[1] = b0.y; kb[2] = b0.z; kb[3] = b0.w; kb[4] = b1.x; kb[5] = b1.y; kb[6] = b1.z; kb[7] = b1.w;
+    kc[0] = c0.x; kc[1] = c0.y; kc[2] = c0.z; kc[3] = c0.w; kc[4] = c1.x; kc[5] = c1.y; kc[6] = c1.z; kc[7] = c1.w;
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  const long long stride = static_cast<long long>(gridDim.x) * rows;
+  for (long long p = blockIdx.x * static_cast<long long>(rows) + r; r < rows && p < P; p += 2 * stride) {
+    const bool two = p + stride < P;
+    const uint4 g0 = ldg_stream(dz + p * CV + cv), f0 = ldg_stream(y + p * CV + cv);
+    uint4 g1 = make_uint4(0, 0, 0, 0), f1 = g1;
+    if (two) {
+      g1 = ldg_stream(dz + (p + stride) * CV + cv);
+      f1 = ldg_stream(y + (p + stride) * CV + cv);
+    }
     float g[8], f[8], o[8];
-    unpack8(ldg_stream(dz + p * CV + cv), g);
-    unpack8(ldg_stream(y + p * CV + cv), f);
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(kA) + cv * 2);
-    const float4 a1 = __ldg(reinterpret_cast<const float4*>(kA) + cv * 2 + 1);
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(kB) + cv * 2);
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(kB) + cv * 2 + 1);
-    const float4 c0 = __ldg(reinterpret_cast<const float4*>(kC) + cv * 2);
-    const float4 c1 = __ldg(reinterpret_cast<const float4*>(kC) + cv * 2 + 1);
-    const float ka[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float kb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    const float kc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    unpack8(g0, g);
+    unpack8(f0, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float d = fmaf(ka[e], g[e], fmaf(kb[e], f[e], kc[e]));
@@ -603,7 +671,29 @@ __global__ void bn_relu_bwd_apply_kernel(const uint4* __restrict__ dz, const uin
       acc[e] += o[e];
     }
     dpre[p * CV + cv] = pack8(o);
-  });
+    if (two) {
+      unpack8(g1, g);
+      unpack8(f1, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = fmaf(ka[e], g[e], fmaf(kb[e], f[e], kc[e]));
+        o[e] = f[e] > 0.f ? d : 0.f;
+        acc[e] += o[e];
+      }
+      dpre[(p + stride) * CV + cv] = pack8(o);
+    }
+  }
+  const int width = CV * 8;
+  if (r < rows) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[r * width + cv * 8 + e] = acc[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < width; i += blockDim.x) {
+    float s = 0.f;
+    for (int rr = 0; rr < rows; ++rr) s += red[rr * width + i];
+    atomicAdd(dbias + i, static_cast<double>(s));
+  }
 }
 cudaError_t bn_relu_bwd_apply(const void* dz, const void* y, void* dpre, const float* kA, const float* kB,
                               const float* kC, double* dbias, long long P, int C, cudaStream_t st) {
@@ -611,7 +701,7 @@ cudaError_t bn_relu_bwd_apply(const void* dz, const void* y, void* dpre, const f
   if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
   const int rows = 256 / CV;
   const size_t smem = static_cast<size_t>(rows) * CV * 8 * sizeof(float);
-  bn_relu_bwd_apply_kernel<<<grid_for(P, rows * 8, 8), 256, smem, st>>>(
+  bn_relu_bwd_apply_kernel<<<grid_for(P, rows * 8, 4), 256, smem, st>>>(
       static_cast<const uint4*>(dz), static_cast<const uint4*>(y), static_cast<uint4*>(dpre), kA, kB, kC,
       dbias, P, CV);
   return cudaGetLastError();
@@ -1023,13 +1113,20 @@ __global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const long long
   const int accumulate = static_cast<int>(J[8]);
   const int local = blockIdx.x - static_cast<int>(J[9]);
   const int tiles_b = static_cast<int>(J[10]);
+  const int transposed = static_cast<int>(J[11]);  // D is [T][ldB][ldA] instead of [T][ldA][ldB]
   const int a0 = (local / tiles_b) * 32, b0 = (local % tiles_b) * 32;
   const int na = min(32, A - a0), nb = min(32, B - b0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pitch = 32 * T + 1;
-  for (int t = 0; t < T; ++t)
-    for (int ar = warp; ar < na; ar += 8)
-      if (lane < nb) tile[ar * pitch + lane * T + t] = D[(static_cast<long long>(t) * ldA + a0 + ar) * ldB + b0 + lane];
+  if (transposed) {
+    for (int t = 0; t < T; ++t)
+      for (int br = warp; br < nb; br += 8)
+        if (lane < na) tile[lane * pitch + br * T + t] = D[(static_cast<long long>(t) * ldB + b0 + br) * ldA + a0 + lane];
+  } else {
+    for (int t = 0; t < T; ++t)
+      for (int ar = warp; ar < na; ar += 8)
+        if (lane < nb) tile[ar * pitch + lane * T + t] = D[(static_cast<long long>(t) * ldA + a0 + ar) * ldB + b0 + lane];
+  }
   __syncthreads();
   for (int ar = warp; ar < na; ar += 8) {
     float* row = grad + (static_cast<long long>(a0 + ar) * B + b0) * T;

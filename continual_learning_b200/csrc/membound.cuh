@@ -23,7 +23,7 @@ cudaError_t im2col3x3_stem(const float* x, void* a, int N, int Cin, int H, int W
 cudaError_t pack_w(const float* src, void* outAB, void* outBA, int A, int B, int T, int ldA, int ldB,
                    int ldB2, int ldA2, int rev, cudaStream_t st);
 cudaError_t unpack_wgrad(const float* D, float* grad, int A, int B, int T, int ldA, int ldB, float alpha,
-                         int accumulate, cudaStream_t st);
+                         int accumulate, int transposed, cudaStream_t st);
 cudaError_t bn_finalize(const double* sum, const double* sq, const float* gamma, const float* beta,
                         float* running_mean, float* running_var, float* mean_out, float* invstd_out,
                         float* scale, float* shift, int C, double count, float eps, float momentum,

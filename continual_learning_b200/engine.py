@@ -85,7 +85,7 @@ class UNetEngine:
             off += s
         nu = len(self.units)
         for i, u in enumerate(self.units):
-            u.gp = views[i].view(64, 64) if u.stem else views[i].view(9, u.cout, u.c0 + u.c1)
+            u.gp = views[i].view(64, 64) if u.stem else views[i].view(9, u.c0 + u.c1, u.cout)
             if u.stem:
                 u.wf = torch.zeros((u.cout, 64), device=dev, dtype=bf16)
                 u.wd = None
@@ -157,9 +157,9 @@ class UNetEngine:
                          A, B, T, ldA, ldB, ldB2, ldA2, rev, t0, tb, 0, 0, 0])
             t0 += n
 
-        def add_unpack(g, D, grad, A, B, T, ldA, ldB):
+        def add_unpack(g, D, grad, A, B, T, ldA, ldB, transposed=0):
             n, tb = self._tiles(A, B)
-            unpack[g].append([D.data_ptr(), grad.data_ptr(), A, B, T, ldA, ldB, one, 0, ut0[g], tb, 0, 0, 0, 0, 0])
+            unpack[g].append([D.data_ptr(), grad.data_ptr(), A, B, T, ldA, ldB, one, 0, ut0[g], tb, transposed, 0, 0, 0, 0])
             ut0[g] += n
 
         def add_cvt(g, src, dst, n):
@@ -175,7 +175,7 @@ class UNetEngine:
             else:
                 ci = u.c0 + u.c1
                 add_pack(w, u.wf, u.wd, u.cout, ci, 9, u.cout, ci, ci, u.cout, 1)
-                add_unpack(g, u.gp, self.gview[w], u.cout, ci, 9, u.cout, ci)
+                add_unpack(g, u.gp, self.gview[w], u.cout, ci, 9, u.cout, ci, transposed=1)
             add_cvt(g, u.dbias, self.gview[u.conv.bias], u.cout)
         for j, (mod, cm, co) in enumerate(self.convT):
             add_pack(mod.weight, self.twd[j], self.twf[j], cm, co, 4, cm, co, co, cm, 0)

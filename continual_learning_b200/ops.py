@@ -85,8 +85,10 @@ def pack_head(w, out_f=None, out_d=None):
     return wf, wd
 
 
-def unpack_wgrad(dpacked, grad, a, b, t, lda, ldb, alpha=1.0, accumulate=False):
-    _lib.call("clk_unpack_wgrad", dpacked, grad, a, b, t, lda, ldb, float(alpha), 1 if accumulate else 0)
+def unpack_wgrad(dpacked, grad, a, b, t, lda, ldb, alpha=1.0, accumulate=False, transposed=False):
+    """grad[A][B][T] = alpha * D[T][lda][ldb]  (transposed: D is [T][ldb][lda], the conv3x3 wgrad layout)."""
+    _lib.call("clk_unpack_wgrad", dpacked, grad, a, b, t, lda, ldb, float(alpha), 1 if accumulate else 0,
+              1 if transposed else 0)
     return grad
 
 
@@ -114,12 +116,12 @@ def conv3x3_dgrad(dy, wd, c0, c1=0, out0=None, out1=None):
 
 
 def conv3x3_wgrad(dy, x0, x1=None, out=None):
-    """returns fp32 [9, Cout, Cin] (accumulates into `out` when given)."""
+    """returns fp32 [9, Cin, Cout] — tap, input channel, output channel (accumulates into `out` when given)."""
     _dev(dy)
     n, h, w, cout = dy.shape
     c0 = x0.shape[3]
     c1 = 0 if x1 is None else x1.shape[3]
-    dw = torch.zeros((9, cout, c0 + c1), device=dy.device, dtype=torch.float32) if out is None else out
+    dw = torch.zeros((9, c0 + c1, cout), device=dy.device, dtype=torch.float32) if out is None else out
     _lib.call("clk_conv3x3_wgrad", dy, cout, x0, c0, x1, c1, dw, n, h, w)
     return dw
 

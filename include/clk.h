@@ -53,14 +53,15 @@ int clk_im2col3x3_stem(const float* x_nchw, void* a, int N, int Cin, int H, int 
  * outAB bf16 [T][ldA][ldB], outBA bf16 [T][ldB2][ldA2] (tap order reversed when rev!=0); either may be NULL. */
 int clk_pack_w(const float* src, void* outAB, void* outBA, int A, int B, int T, int ldA, int ldB,
                int ldB2, int ldA2, int rev, clk_stream_t st);
-/* grad[A][B][T] (=|+=) alpha * D[T][ldA][ldB]   (D = packed fp32 weight gradient) */
+/* grad[A][B][T] (=|+=) alpha * D[T][ldA][ldB]   (D = packed fp32 weight gradient);
+ * transposed != 0: D is [T][ldB][ldA] (the conv3x3 wgrad layout [9][Cin][Cout] with A = Cout, B = Cin). */
 int clk_unpack_wgrad(const float* D, float* grad, int A, int B, int T, int ldA, int ldB, float alpha,
-                     int accumulate, clk_stream_t st);
+                     int accumulate, int transposed, clk_stream_t st);
 
 /* Batched (table-driven) forms: ONE launch for every layer of the model. `jobs` is a device array of
  * int64[16] rows (pointers and ints widened to int64, alpha as the bit pattern of a double):
  *   pack:    {src, outAB, outBA, A, B, T, ldA, ldB, ldB2, ldA2, rev, tile0, tiles_b}
- *   unpack:  {D, grad, A, B, T, ldA, ldB, alpha, accumulate, tile0, tiles_b}
+ *   unpack:  {D, grad, A, B, T, ldA, ldB, alpha, accumulate, tile0, tiles_b, transposed}
  *   convert: {src_f64, dst_f32, n, ld_group, groups, alpha, accumulate}   (one block per row)
  * tile0 = index of the job's first 32x32 tile in the launch grid, tiles_b = ceil(B/32). */
 int clk_pack_w_multi(const void* jobs, int njobs, int total_tiles, int max_T, clk_stream_t st);
@@ -80,7 +81,8 @@ int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void
  * wd bf16 [9][C0+C1][Cout] (clk_pack_w outBA, rev=1); writes dx0 [..][C0] and dx1 [..][C1]. */
 int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C0, void* dx1, int C1,
                       int N, int H, int W, clk_stream_t st);
-/* wgrad: dw fp32 [9][Cout][C0+C1] += sum_pixels dy (x) shifted x.  Caller zeroes dw. */
+/* wgrad: dw fp32 [9][C0+C1][Cout] += sum_pixels shifted x (x) dy  (tap, input channel, output channel).
+ * Caller zeroes dw; clk_unpack_wgrad(..., transposed=1) turns it into the PyTorch [Cout][Cin][3][3] layout. */
 int clk_conv3x3_wgrad(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw,
                       int N, int H, int W, clk_stream_t st);
 /* plain GEMM out[P][.] = a[P][K] * w[Npad][K]^T (+bias, ReLU, stats): the im2col'ed stem conv

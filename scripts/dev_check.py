@@ -104,10 +104,10 @@ def run_group(g):
             xr = xh.float().permute(0, 3, 1, 2).requires_grad_(False)
             wref = torch.zeros(co, c0 + c1, 3, 3, device=dev, requires_grad=True)
             F.conv2d(xr, wref, padding=1).backward(dyh.float().permute(0, 3, 1, 2))
-            got = dw.reshape(3, 3, co, c0 + c1).permute(2, 3, 0, 1)
+            got = dw.reshape(3, 3, c0 + c1, co).permute(3, 2, 0, 1)
             report(f"conv3x3_wgrad n={n} {h}x{w_} {c0}+{c1}->{co}", rel(got, wref.grad), 5e-3)
             g2 = torch.empty(co, c0 + c1, 3, 3, device=dev)
-            ops.unpack_wgrad(dw, g2, co, c0 + c1, 9, co, c0 + c1)
+            ops.unpack_wgrad(dw, g2, co, c0 + c1, 9, co, c0 + c1, transposed=True)
             report("  unpack_wgrad", rel(g2, got), 1e-7)
         for (P, cu, ct) in [(1000, 64, 64), (5000, 128, 64), (777, 64, 128)]:
             u, t = bf(rnd(P, cu)), bf(rnd(P, ct))

@@ -71,7 +71,7 @@ def main():
         dy = torch.randn(B, h, w, co, device=dev).to(bf16)
         dx0 = torch.empty_like(x0)
         dx1 = torch.empty_like(x1) if c1 else None
-        dw = torch.zeros(9, co, c0 + c1, device=dev)
+        dw = torch.zeros(9, c0 + c1, co, device=dev)
         gf = 2.0 * B * h * w * co * (c0 + c1) * 9 / 1e9
         row = f"{nm:10s} {f'{c0}+{c1}->{co} @{h}x{w}':28s} {gf:8.1f} |"
         for kind, fn in (("fprop", lambda: ops.conv3x3_fprop(x0, x1, wf, bias, relu=True, stats=(ss, sq), out=y)),

@@ -126,7 +126,7 @@ def _check_conv3x3_wgrad(ops, n, h, w, c0, c1, co):
     wref = torch.zeros(co, c0 + c1, 3, 3, requires_grad=True)
     F.conv2d(x, wref, padding=1).backward(dy)
     grad = torch.empty(co, c0 + c1, 3, 3, device="cuda")
-    ops.unpack_wgrad(dw, grad, co, c0 + c1, 9, co, c0 + c1)
+    ops.unpack_wgrad(dw, grad, co, c0 + c1, 9, co, c0 + c1, transposed=True)
     assert rel(grad, wref.grad) <= 2e-5  # fp32 accumulate, fp32 output, split-K order only
 
 
