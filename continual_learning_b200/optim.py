@@ -39,10 +39,14 @@ class FusedAdam(torch.optim.Optimizer):
         self._tables[gi] = (key, t, b, len(blocks))
         return t, b, len(blocks)
 
+    default_grad_scale = 1.0  # set to 1/world by parallel.attach()
+
     @torch.no_grad()
-    def step(self, closure=None, grad_scale=1.0, hyper_dev=None):
+    def step(self, closure=None, grad_scale=None, hyper_dev=None):
         """hyper_dev: optional device float[4] {lr, bc1, bc2_sqrt, gscale} (see `hyper_values`) read by the
         kernel instead of the host scalars — lets a captured CUDA graph be replayed."""
+        if grad_scale is None:
+            grad_scale = self.default_grad_scale
         loss = None
         if closure is not None:
             with torch.enable_grad():

@@ -107,3 +107,13 @@ def all_reduce_confusion(conf, correct, group=None):
     buf = torch.cat([conf.reshape(-1), correct.reshape(-1)])
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return buf[:-1].view_as(conf), buf[-1:]
+
+
+def attach(model, optimizer, n_buckets=4):
+    """module path (UNet + loss.backward() + optimizer.step()): all-reduce the flat gradient buffer inside the
+    U-Net backward (decoder buckets overlap the encoder backward) and fold the 1/world scale into FusedAdam."""
+    names = [k for k, _ in model.named_parameters()]
+    comm = GradAllReduce([p.numel() for p in model.parameters()], names, n_buckets=n_buckets)
+    model.engine.comm = comm
+    optimizer.default_grad_scale = 1.0 / comm.world_size
+    return comm

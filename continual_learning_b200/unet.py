@@ -51,7 +51,10 @@ class _UNetFn(torch.autograd.Function):
             g = grad_out.permute(0, 2, 3, 1)
             dl = torch.zeros((*g.shape[:3], 64), device=g.device, dtype=torch.bfloat16)
             dl[..., :g.shape[3]] = g
-        views = eng.backward(dl)
+        comm = getattr(eng, "comm", None)
+        views = eng.backward(dl, after_decoder=(lambda: comm.start_decoder(eng.G)) if comm is not None else None)
+        if comm is not None:
+            comm.finish(eng.G)
         grads = []
         for p, v in zip(eng.params, views):
             # autograd accumulates `p.grad += g` when a grad already exists; never alias then

@@ -1,0 +1,82 @@
+"""CPU: the data-parallel host logic (batch sharding, gradient buckets, bucketed all-reduce, confusion-matrix
+reduction) with world_size 2 over gloo.  The kernels are not involved; the N>1 GPU path runs the same code
+over NCCL."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from continual_learning_b200 import parallel
+from oracle.unet_ref import make_state_dict, param_names
+
+
+def _names_numels():
+    sd = make_state_dict(0)
+    names = param_names(sd)
+    return names, [sd[k].numel() for k in names]
+
+
+def test_bucket_bounds_cover_the_flat_buffer_in_backward_order():
+    names, numels = _names_numels()
+    bounds = parallel.bucket_bounds(numels, names, n_buckets=4)
+    total = sum(numels)
+    # disjoint, complete
+    spans = sorted(bounds)
+    assert spans[0][0] == 0 and spans[-1][1] == total
+    for (a0, b0), (a1, b1) in zip(spans, spans[1:]):
+        assert b0 == a1
+    # launch order: head/decoder buckets first (their gradients are final first), encoder last
+    enc_end = sum(n for k, n in zip(names, numels) if k.startswith("enc"))
+    assert bounds[-1] == (0, enc_end)
+    assert bounds[0][1] == total
+    assert all(bounds[i][0] >= bounds[i + 1][0] for i in range(len(bounds) - 2))
+
+
+def test_shard_batch():
+    x = torch.arange(8).view(8, 1)
+    assert parallel.shard_batch(x, 1, 4).flatten().tolist() == [2, 3]
+    with pytest.raises(ValueError):
+        parallel.shard_batch(x, 0, 3)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    r, _, w = parallel.init_from_env(backend="gloo")
+    names, numels = _names_numels()
+    comm = parallel.GradAllReduce(numels, names, n_buckets=4)
+    flat = torch.full((sum(numels),), float(rank + 1))
+    flat[::1000] += torch.arange(flat[::1000].numel(), dtype=torch.float32) * (rank + 1)
+    expect = torch.full_like(flat, 3.0)
+    expect[::1000] += torch.arange(flat[::1000].numel(), dtype=torch.float32) * 3
+    comm.start_decoder(flat)   # head + decoder buckets while "the encoder backward still runs"
+    enc_end = comm.bounds[-1][1]
+    flat[:enc_end] *= 1.0      # encoder gradients become final
+    comm.finish(flat)
+    ok = torch.equal(flat, expect)
+    conf = torch.full((21, 21), rank + 1, dtype=torch.int64)
+    correct = torch.tensor([10 * (rank + 1)], dtype=torch.int64)
+    conf2, correct2 = parallel.all_reduce_confusion(conf, correct)
+    ok = ok and bool((conf2 == 3).all()) and int(correct2) == 30 and comm.world_size == 2 and (r, w) == (rank, world)
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_two_ranks_gloo():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: True, 1: True}
