@@ -547,9 +547,12 @@ __global__ void __launch_bounds__(256, 4)
   float acc[16];
 #pragma unroll
   for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+  // descending pixel order: the producer of dz (a dgrad epilogue) wrote it in ascending tile order, so the tail
+  // is what is still in L2; bn_relu_bwd_apply then walks ascending and finds the head this kernel read last
   const long long stride = static_cast<long long>(gridDim.x) * rows;
-  for (long long p = blockIdx.x * static_cast<long long>(rows) + r; r < rows && p < P; p += 2 * stride) {
-    const bool two = p + stride < P;
+  for (long long q = blockIdx.x * static_cast<long long>(rows) + r; r < rows && q < P; q += 2 * stride) {
+    const bool two = q + stride < P;
+    const long long p = P - 1 - q - (two ? stride : 0);
     const uint4 g0 = ldg_stream(dz + p * CV + cv), f0 = ldg_stream(y + p * CV + cv);
     uint4 g1 = make_uint4(0, 0, 0, 0), f1 = g1;
     if (two) {
@@ -652,6 +655,8 @@ __global__ void __launch_bounds__(256, 4)
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  // ascending pixel order; bn_bwd_reduce walked the same two tensors in DESCENDING order just before, so the
+  // head of dz / y is what is still resident in the 126 MB L2
   const long long stride = static_cast<long long>(gridDim.x) * rows;
   for (long long p = blockIdx.x * static_cast<long long>(rows) + r; r < rows && p < P; p += 2 * stride) {
     const bool two = p + stride < P;

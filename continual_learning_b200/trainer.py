@@ -158,20 +158,20 @@ class Trainer:
                     self._dump_samples(inputs, labels, output_label, epoch, I)
                     if self.rank == 0:
                         elapsed = str(timedelta(seconds=time.time() - start_mini_batch))
-                        print(f"Iteration : [{epoch}/{cfg.n_iters}]\\tminibatch: [{I}/{iters_per_epoch}]\\t"
-                              f"Mini Batch Time : {elapsed}\\tPixel Accuracy : {pixel_accuracy:.4f}\\t"
-                              f"Pixel ACC2 : {float(pixel_acc):.4f}\\tPixel MAX CLASS : {float(max_per_class_acc):.4f}\\t"
-                              f"Class Accuracy : {float(pixel_acc_class):.4f}\\tMean  : {float(mean):.4f}\\t"
-                              f"Mean  : {float(mean_IU_2):.4f}\\tMini Batch Loss : {curr_loss:.4f}\\t")
+                        print(f"Iteration : [{epoch}/{cfg.n_iters}]\tminibatch: [{I}/{iters_per_epoch}]\t"
+                              f"Mini Batch Time : {elapsed}\tPixel Accuracy : {pixel_accuracy:.4f}\t"
+                              f"Pixel ACC2 : {float(pixel_acc):.4f}\tPixel MAX CLASS : {float(max_per_class_acc):.4f}\t"
+                              f"Class Accuracy : {float(pixel_acc_class):.4f}\tMean  : {float(mean):.4f}\t"
+                              f"Mean  : {float(mean_IU_2):.4f}\tMini Batch Loss : {curr_loss:.4f}\t")
             if (epoch + 1) % cfg.log_step == 0 and self.rank == 0 and print_number:
-                print(f"Iteration : [{epoch}/{cfg.n_iters}]\\tEpoch Time : {timedelta(seconds=time.time() - start_epoch)}\\t"
-                      f"Total Time : {timedelta(seconds=time.time() - since)}\\t"
-                      f"Accuracy Epoch : {pixel_accuracy_epoch / print_number}\\t"
-                      f"Loss Epoch: {running_loss / print_number:.4f}\\t")
+                print(f"Iteration : [{epoch}/{cfg.n_iters}]\tEpoch Time : {timedelta(seconds=time.time() - start_epoch)}\t"
+                      f"Total Time : {timedelta(seconds=time.time() - since)}\t"
+                      f"Accuracy Epoch : {pixel_accuracy_epoch / print_number}\t"
+                      f"Loss Epoch: {running_loss / print_number:.4f}\t")
             if (epoch + 1) % 150 == 0:
                 test_acc = self.test()
                 if self.rank == 0:
-                    print(f"Iteration : [{epoch}/{cfg.n_iters}]\\tTest Accuracy  : {test_acc}\\t")
+                    print(f"Iteration : [{epoch}/{cfg.n_iters}]\tTest Accuracy  : {test_acc}\t")
             epoch += 1
             self.save_network(self.model, "UNET_VOC", "latest", [0], epoch, self.optim, self.scheduler)
             if epoch % 10 == 0:
