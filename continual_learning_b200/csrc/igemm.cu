@@ -270,7 +270,24 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
             }
           }
         } else {
-          if (valid) {
+          const bool dense_rows = p.g.mode == ADDR_LINEAR && !p.shuffle && ld == p.n_store && BN == 32;
+          if (dense_rows) {
+            // fp32 rows of n_store (< 32) columns are contiguous in memory across the 32 consecutive pixels of a
+            // warp: stage them in shared memory and write the whole 32*n_store block with coalesced stores
+            const int ns = p.n_store;
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ns) scratch[lane * ns + j] = f[j];
+            __syncwarp();
+            OutT* wbase = dst + (static_cast<long long>(b1) + q * 32) * ld;  // first pixel row of this warp
+            for (int idx = lane; idx < 32 * ns; idx += 32) {
+              const int r = idx / ns;
+              if ((vmask >> r) & 1u) wbase[idx] = scratch[idx];
+            }
+            __syncwarp();
+          } else if (valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (n0 + chunk * 32 + j < p.n_store) drow[chunk * 32 + j] = f[j];

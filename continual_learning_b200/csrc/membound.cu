@@ -325,7 +325,7 @@ cudaError_t bn_finalize(const double* sum, const double* sq, const float* gamma,
 __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, uint4* __restrict__ z,
                                                         const float* __restrict__ scale,
                                                         const float* __restrict__ shift, long long nvec, int CV) {
-  const int cv = threadIdx.x % CV;
+  const int cv = CV - 1 - (threadIdx.x % CV);  // mirrored traversal (see below)
   float a[8], c[8];
   {
     const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale) + cv * 2);
@@ -335,9 +335,13 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
     a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
     c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
   }
+  // descending order: the conv epilogue wrote y in ascending tile order (its tail is still in L2), and the next
+  // conv reads z in ascending order (the head, written last here, is then still in L2).  nvec is a multiple of
+  // CV and so is the stride, hence the mirrored index keeps the thread's channel column (CV-1-cv) fixed.
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec; i += 2 * stride) {
-    const bool two = i + stride < nvec;
+  for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < nvec; j += 2 * stride) {
+    const bool two = j + stride < nvec;
+    const long long i = nvec - 1 - j - (two ? stride : 0);
     const uint4 v0 = ldg_stream(y + i);
     const uint4 v1 = two ? ldg_stream(y + i + stride) : make_uint4(0, 0, 0, 0);
     float f[8];
