@@ -54,6 +54,9 @@ class UNetEngine:
         self._dev = None
         self._wver = None
         self._job_ptrs = None
+        self._side = None
+        self._pending = []
+        self.use_side_stream = True
         self.training_fwd = True
         self.logits = None
 
@@ -193,6 +196,7 @@ class UNetEngine:
         self.cvt_jobs = [(dev_table(cvt[g]), len(cvt[g])) for g in range(2)]
 
     def _flush_grads(self, g):
+        self._join()  # weight gradients run on the side stream
         tab, n, tiles = self.unpack_jobs[g]
         _lib.call("clk_unpack_wgrad_multi", tab, n, tiles, 9)
         tab, n = self.cvt_jobs[g]
@@ -272,19 +276,53 @@ class UNetEngine:
         ops.bn_bwd_finalize(u.s1, u.s2, bn.weight.detach(), mean, invstd, self.gview[bn.weight], self.gview[bn.bias],
                             ka, kb, kc, n * h * w, training=self.training_fwd)
         dpre = ops.bn_relu_bwd_apply(dz, u.y, ka, kb, kc, u.dbias)
-        if u.stem:
-            ops.gemm_wgrad(dpre, u.x0, out=u.gp)
-            return None, None
-        ops.conv3x3_wgrad(dpre, u.x0, u.x1, out=u.gp)
-        if not need_dx:
+        # the weight gradient only feeds the optimiser: run it on the side stream so that it overlaps the dgrad of
+        # this layer and the (HBM-bound) BatchNorm backward of the next one
+        with self._fork(dpre):
+            if u.stem:
+                ops.gemm_wgrad(dpre, u.x0, out=u.gp)
+            else:
+                ops.conv3x3_wgrad(dpre, u.x0, u.x1, out=u.gp)
+        if u.stem or not need_dx:
             return None, None
         return ops.conv3x3_dgrad(dpre, u.wd, u.c0, u.c1)
 
     def _convT_bwd(self, j, dy):
         mod, cm, co = self.convT[j]
-        ops.convT_wgrad(self.tin[j], dy, out=self.tgp[j])
-        ops.channel_sum(dy, self.tdbias[j])
+        with self._fork(dy):
+            ops.convT_wgrad(self.tin[j], dy, out=self.tgp[j])
+            ops.channel_sum(dy, self.tdbias[j])
         return ops.convT_dgrad(dy, self.twd[j])
+
+    # ------------------------------------------------------------------ side stream for weight gradients
+    class _Fork:
+        def __init__(self, eng, keep):
+            self.eng, self.keep = eng, keep
+
+        def __enter__(self):
+            eng = self.eng
+            if not eng.use_side_stream:
+                return self
+            if eng._side is None:
+                eng._side = torch.cuda.Stream()
+            eng._pending.append(self.keep)  # keep the operand alive until the join (it is read on another stream)
+            eng._side.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(eng._side)
+            self.ctx.__enter__()
+            return self
+
+        def __exit__(self, *exc):
+            if self.eng.use_side_stream:
+                self.ctx.__exit__(*exc)
+            return False
+
+    def _fork(self, keep):
+        return UNetEngine._Fork(self, keep)
+
+    def _join(self):
+        if self.use_side_stream and self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)
+        self._pending = []
 
     def backward(self, dlogits, after_decoder=None):
         """dlogits: bf16 [N, H, W, 64] (columns >= num_classes zero). Fills the flat gradient buffer and
@@ -296,8 +334,9 @@ class UNetEngine:
         self.acc_b.zero_()
         self.Gp.zero_()
         # 1x1 head (models/unet.py:72)
-        ops.gemm_wgrad(dlogits, U[17].z, out=self.hgp)
-        ops.channel_sum(dlogits, self.hdbias)
+        with self._fork(dlogits):
+            ops.gemm_wgrad(dlogits, U[17].z, out=self.hgp)
+            ops.channel_sum(dlogits, self.hdbias)
         dz = ops.gemm_fprop(dlogits, self.hwd, None, self.m.conv_dim)
         dz, _ = self._unit_bwd(U[17], dz)
         skip_grads = []
