@@ -241,11 +241,13 @@ def run_b200(args):
     # ---- per-kernel timing of one eager step (CUDA events around every clk_* launch) -> roofline
     ts_prof = clk.TrainStep(model, opt, use_graph=False, comm=comm)
     ts_prof.step_count = ts.step_count
+    model.engine.use_side_stream = False  # serialise the weight-gradient stream: one kernel at a time under the events
     ts_prof.step(*devb[0])
     torch.cuda.synchronize()
     _lib.start_profile()
     ts_prof.step(*devb[1])
     prof = _lib.stop_profile()
+    model.engine.use_side_stream = True
     igemm_names = [k for k in prof if k.startswith(("clk_conv3x3_", "clk_gemm_", "clk_convT2x2_"))]
     igemm_ms = sum(prof[k][1] for k in igemm_names)
     igemm_n = sum(prof[k][0] for k in igemm_names)

@@ -813,17 +813,10 @@ __global__ void __launch_bounds__(kC3Threads, 1)
         named_bar_sync(2, kC3EpiThreads);
         bias_nt = nt;
       }
-      __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.dst0);
-      int ld = p.ldc0, colbase = n0;
-      if (p.split_c > 0 && n0 >= p.split_c) {
-        dst = reinterpret_cast<__nv_bfloat16*>(p.dst1);
-        ld = p.ldc1;
-        colbase = n0 - p.split_c;
-      }
       const int h = ty * 16 + (mrow >> 3);
       const int w = tx * 16 + j * 8 + (mrow & 7);
       const bool valid = h < p.H && w < p.W;
-      __nv_bfloat16* drow = dst + (valid ? (static_cast<long long>(n) * p.H + h) * p.W + w : 0) * ld + colbase;
+      const long long pixoff = valid ? (static_cast<long long>(n) * p.H + h) * p.W + w : 0;
       mbar_wait(&acc_full[acc], pacc);
       tc_fence_after();
 #pragma unroll 1
@@ -846,7 +839,13 @@ __global__ void __launch_bounds__(kC3Threads, 1)
           pk[2 * jj + 1] = pack_bf16x2(x2, x3);
         }
         if (valid && in_store) {
-          uint4* o = reinterpret_cast<uint4*>(drow + chunk * 32);
+          // two destinations (dgrad of a concat input): the split is a multiple of 32 columns, so it is decided
+          // per 32-column chunk and an N tile may straddle it
+          const int gc = n0 + chunk * 32;
+          __nv_bfloat16* orow = (p.split_c > 0 && gc >= p.split_c)
+                                    ? reinterpret_cast<__nv_bfloat16*>(p.dst1) + pixoff * p.ldc1 + (gc - p.split_c)
+                                    : reinterpret_cast<__nv_bfloat16*>(p.dst0) + pixoff * p.ldc0 + gc;
+          uint4* o = reinterpret_cast<uint4*>(orow);
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj)
             o[jj] = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);

@@ -119,6 +119,18 @@ int clk_bn_apply(const void* y, void* z, const float* scale, const float* shift,
  * scale == NULL: pooling only (z untouched). */
 int clk_bn_apply_pool(const void* y, void* z, void* pooled, void* idx, const float* scale,
                       const float* shift, int N, int H, int W, int C, clk_stream_t st);
+/* Fused-finalize forms used by the step (one launch instead of two): the per-channel coefficients are computed
+ * from the raw sums in the kernel prologue; block 0 writes mean / invstd / running stats (resp. dgamma / dbeta). */
+int clk_bn_apply_fused(const void* y, void* z, const double* sum, const double* sq, const float* gamma,
+                       const float* beta, float* running_mean, float* running_var, float* mean_out, float* invstd_out,
+                       long long P, int C, double count, float eps, float momentum, int training, clk_stream_t st);
+int clk_bn_apply_pool_fused(const void* y, void* z, void* pooled, void* idx, const double* sum, const double* sq,
+                            const float* gamma, const float* beta, float* running_mean, float* running_var,
+                            float* mean_out, float* invstd_out, int N, int H, int W, int C, double count, float eps,
+                            float momentum, int training, clk_stream_t st);
+int clk_bn_relu_bwd_apply_fused(const void* dz, const void* y, void* dpre, const double* s1, const double* s2,
+                                const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                                double* dbias, long long P, int C, double count, int training, clk_stream_t st);
 /* din = scatter(dpooled by idx) + skip (skip may be NULL): max-pool backward fused with the
  * skip-connection gradient sum. */
 int clk_maxpool_bwd_add(const void* dpooled, const void* idx, const void* skip, void* din, int N, int H,
