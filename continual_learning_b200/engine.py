@@ -57,6 +57,8 @@ class UNetEngine:
         self._side = None
         self._pending = []
         self.use_side_stream = True
+        self.fuse_bn = True      # finalize folded into the apply kernels
+        self.side_pack = True    # late-layer weight packing on the side stream
         self.training_fwd = True
         self.logits = None
 
@@ -138,7 +140,10 @@ class UNetEngine:
         tab, n, tiles = self.pack_jobs[0]
         _lib.call("clk_pack_w_multi", tab, n, tiles, 9)
         tab, n, tiles = self.pack_jobs[1]
-        with self._fork(None):
+        if self.side_pack:
+            with self._fork(None):
+                _lib.call("clk_pack_w_multi", tab, n, tiles, 9)
+        else:
             _lib.call("clk_pack_w_multi", tab, n, tiles, 9)
         self._wver = ver
 
@@ -219,6 +224,16 @@ class UNetEngine:
         else:
             u.y = ops.conv3x3_fprop(x0, x1, u.wf, bias, relu=True, stats=stats)
         bn = u.bn
+        if not self.fuse_bn:
+            mean, invstd, scale, shift = u.vec[0], u.vec[1], u.vec[2], u.vec[3]
+            ops.bn_finalize(u.s_sum, u.s_sq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, mean,
+                            invstd, scale, shift, n * h * w, eps=bn.eps,
+                            momentum=0.1 if bn.momentum is None else bn.momentum, training=training)
+            if pool:
+                u.z, u.pooled, u.idx = ops.bn_apply_pool(u.y, scale, shift)
+            else:
+                u.z, u.pooled, u.idx = ops.bn_apply(u.y, scale, shift), None, None
+            return u.z
         u.z, u.pooled, u.idx = ops.bn_apply_fused(
             u.y, u.s_sum, u.s_sq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, u.vec[0],
             u.vec[1], n * h * w, eps=bn.eps, momentum=0.1 if bn.momentum is None else bn.momentum, training=training,
@@ -274,7 +289,15 @@ class UNetEngine:
         n, h, w = dz.shape[0], dz.shape[1], dz.shape[2]
         bn = u.bn
         ops.bn_bwd_reduce(dz, u.y, u.s1, u.s2)
-        dpre = ops.bn_relu_bwd_apply_fused(dz, u.y, u.s1, u.s2, bn.weight.detach(), u.vec[0], u.vec[1],
+        if not self.fuse_bn:
+            ka, kb, kc = u.vec[4], u.vec[5], u.vec[6]
+            ops.bn_bwd_finalize(u.s1, u.s2, bn.weight.detach(), u.vec[0], u.vec[1], self.gview[bn.weight],
+                                self.gview[bn.bias], ka, kb, kc, n * h * w, training=self.training_fwd)
+            dpre = ops.bn_relu_bwd_apply(dz, u.y, ka, kb, kc, u.dbias)
+        else:
+            dpre = self._bn_bwd_fused(u, dz, n * h * w)
+        if False:
+            dpre = ops.bn_relu_bwd_apply_fused(dz, u.y, u.s1, u.s2, bn.weight.detach(), u.vec[0], u.vec[1],
                                            self.gview[bn.weight], self.gview[bn.bias], u.dbias, n * h * w,
                                            training=self.training_fwd)
         # the weight gradient only feeds the optimiser: run it on the side stream so that it overlaps the dgrad of
@@ -287,6 +310,12 @@ class UNetEngine:
         if u.stem or not need_dx:
             return None, None
         return ops.conv3x3_dgrad(dpre, u.wd, u.c0, u.c1)
+
+    def _bn_bwd_fused(self, u, dz, count):
+        bn = u.bn
+        return ops.bn_relu_bwd_apply_fused(dz, u.y, u.s1, u.s2, bn.weight.detach(), u.vec[0], u.vec[1],
+                                           self.gview[bn.weight], self.gview[bn.bias], u.dbias, count,
+                                           training=self.training_fwd)
 
     def _convT_bwd(self, j, dy):
         mod, cm, co = self.convT[j]

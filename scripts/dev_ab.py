@@ -1,0 +1,48 @@
+"""A/B timing of engine options on ONE box (CUDA-graph TrainStep at the benchmark shape). Developer tool."""
+import itertools
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import continual_learning_b200 as clk
+from oracle.data import uniform_batch
+
+
+def time_cfg(flags, tune, steps=40):
+    from continual_learning_b200 import _lib
+    for k, v in tune.items():
+        _lib.set_tuning(k, v)
+    torch.manual_seed(0)
+    m = clk.UNet(21).cuda().train()
+    for k, v in flags.items():
+        setattr(m.engine, k, v)
+    opt = clk.FusedAdam(m.parameters(), lr=1e-4, betas=(0.5, 0.99))
+    ts = clk.TrainStep(m, opt, use_graph=True)
+    bx, by = uniform_batch(1, 16, 256, 256)
+    bx, by = bx.cuda(), by.cuda()
+    for _ in range(5):
+        ts.step(bx, by)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        ts.step(bx, by)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+if __name__ == "__main__":
+    base = dict(use_side_stream=True, fuse_bn=True, side_pack=True)
+    variants = [("all on", {}, {}), ("no fuse_bn", dict(fuse_bn=False), {}), ("no side_pack", dict(side_pack=False), {}),
+                ("no side stream", dict(use_side_stream=False, side_pack=False), {}),
+                ("all on (repeat)", {}, {})]
+    for extra in sys.argv[1:]:
+        k, v = extra.split("=")
+        variants.append((extra, {}, {k: int(v)}))
+    for name, fl, tune in variants:
+        f = dict(base)
+        f.update(fl)
+        print(f"{name:24s} {time_cfg(f, tune):8.3f} ms/step", flush=True)
