@@ -57,7 +57,8 @@ class UNetEngine:
         self._side = None
         self._pending = []
         self.use_side_stream = True
-        self.fuse_bn = True      # finalize folded into the apply kernels
+        self._forked = False
+        self.fuse_bn = False     # finalize folded into the apply kernels: measured 0.17 ms/step SLOWER (fp64 prologue per block)
         self.side_pack = True    # late-layer weight packing on the side stream
         self.training_fwd = True
         self.logits = None
@@ -338,6 +339,7 @@ class UNetEngine:
             if self.keep is not None:
                 eng._pending.append(self.keep)  # keep the operand alive until the join (read on another stream)
             eng._side.wait_stream(torch.cuda.current_stream())
+            eng._forked = True
             self.ctx = torch.cuda.stream(eng._side)
             self.ctx.__enter__()
             return self
@@ -351,8 +353,9 @@ class UNetEngine:
         return UNetEngine._Fork(self, keep)
 
     def _join(self):
-        if self.use_side_stream and self._side is not None:
+        if self._forked and self._side is not None:  # only when work was forked since the last join
             torch.cuda.current_stream().wait_stream(self._side)
+        self._forked = False
         self._pending = []
 
     def backward(self, dlogits, after_decoder=None):

@@ -35,10 +35,11 @@ def time_cfg(flags, tune, steps=40):
 
 
 if __name__ == "__main__":
-    base = dict(use_side_stream=True, fuse_bn=True, side_pack=True)
-    variants = [("all on", {}, {}), ("no fuse_bn", dict(fuse_bn=False), {}), ("no side_pack", dict(side_pack=False), {}),
+    base = dict(use_side_stream=True, fuse_bn=False, side_pack=True)
+    variants = [("default", {}, {}), ("fuse_bn", dict(fuse_bn=True), {}), ("no side_pack", dict(side_pack=False), {}),
                 ("no side stream", dict(use_side_stream=False, side_pack=False), {}),
-                ("all on (repeat)", {}, {})]
+                ("default (repeat)", {}, {}), ("fprop_bn=64", {}, {"fprop_bn": 64}), ("conv3 generic only", {}, {"conv3_v2": 0}),
+                ("conv3 halo everywhere", {}, {"conv3_v2": 2}), ("wgrad generic", {}, {"wgrad_v2": 0}), ("default (again)", {}, {"fprop_bn": 0, "conv3_v2": 1, "wgrad_v2": 1})]
     for extra in sys.argv[1:]:
         k, v = extra.split("=")
         variants.append((extra, {}, {k: int(v)}))
