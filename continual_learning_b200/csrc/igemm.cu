@@ -718,29 +718,52 @@ __global__ void __launch_bounds__(kC3Threads, 1)
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
+    // Two cursors over the flattened (tile, chunk) items: the halo cursor (A ring, 2 stages) and the weight
+    // cursor (B ring, 9 tiles per item).  Both are advanced by non-blocking polls, so the halo tile of item i+1 is
+    // requested the moment item i-1 releases its stage — a full item (9*8 MMAs) ahead of its first use — instead
+    // of queueing behind the nine weight loads of item i.
     if (elect_one()) {
-      uint32_t ia = 0, ib = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int m = t % p.m_tiles, nt = t / p.m_tiles;
-        const int tx = m % p.tiles_w;
-        const int r = m / p.tiles_w;
-        const int ty = r % p.tiles_h;
-        const int n = r / p.tiles_h;
-        for (int ch = 0; ch < kc; ++ch) {
+      uint32_t ia = 0, ib = 0;                 // A loads / B loads issued so far
+      int tA = blockIdx.x, chA = 0;            // next halo tile to request
+      int tB = blockIdx.x, chB = 0, tapB = 0;  // next weight tile to request
+      uint32_t idle = 0;
+      while (tB < total) {
+        if (++idle > CLK_SPIN_LIMIT) __trap();  // protocol bug: fail the launch instead of hanging the GPU
+        if (tA < total && ia <= ib / 9 + 1) {
           const uint32_t sa = ia & 1, pa = (ia >> 1) & 1;
-          mbar_wait(&a_empty[sa], pa ^ 1);
-          mbar_arrive_expect_tx(&a_full[sa], kC3ABytes);
-          if (ch < p.kc0)
-            tma_load_5d(sA + sa * kC3ABytes, &mapA0, &a_full[sa], ch * 64, tx * 16 - 1, ty * 16 - 1, n, 0);
-          else
-            tma_load_5d(sA + sa * kC3ABytes, &mapA1, &a_full[sa], (ch - p.kc0) * 64, tx * 16 - 1, ty * 16 - 1, n, 0);
-          ++ia;
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t sb = ib % NB, pb = (ib / NB) & 1;
-            mbar_wait(&b_empty[sb], pb ^ 1);
+          if (mbar_try_wait(&a_empty[sa], pa ^ 1)) {
+            const int m = tA % p.m_tiles;
+            const int tx = m % p.tiles_w;
+            const int r = m / p.tiles_w;
+            const int ty = r % p.tiles_h;
+            const int n = r / p.tiles_h;
+            mbar_arrive_expect_tx(&a_full[sa], kC3ABytes);
+            if (chA < p.kc0)
+              tma_load_5d(sA + sa * kC3ABytes, &mapA0, &a_full[sa], chA * 64, tx * 16 - 1, ty * 16 - 1, n, 0);
+            else
+              tma_load_5d(sA + sa * kC3ABytes, &mapA1, &a_full[sa], (chA - p.kc0) * 64, tx * 16 - 1, ty * 16 - 1, n, 0);
+            ++ia;
+            idle = 0;
+            if (++chA == kc) {
+              chA = 0;
+              tA += gridDim.x;
+            }
+          }
+        }
+        {
+          const uint32_t sb = ib % NB, pb = (ib / NB) & 1;
+          if (mbar_try_wait(&b_empty[sb], pb ^ 1)) {
             mbar_arrive_expect_tx(&b_full[sb], B_BYTES);
-            tma_load_3d(sB + sb * B_BYTES, &mapB, &b_full[sb], ch * 64, nt * BN, tap);
+            tma_load_3d(sB + sb * B_BYTES, &mapB, &b_full[sb], chB * 64, (tB / p.m_tiles) * BN, tapB);
             ++ib;
+            idle = 0;
+            if (++tapB == 9) {
+              tapB = 0;
+              if (++chB == kc) {
+                chB = 0;
+                tB += gridDim.x;
+              }
+            }
           }
         }
       }
