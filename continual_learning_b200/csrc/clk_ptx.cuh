@@ -190,4 +190,21 @@ __device__ __forceinline__ float bf16hi_to_f32(uint32_t v) {
   return __uint_as_float(v & 0xFFFF0000u);
 }
 
+// Column sums of a 32x32 tile held one ROW per lane (f[j] = element (lane, j)): butterfly transpose-reduce with
+// 31 shuffles; on return f[0] of lane l is the sum over the 32 rows of column l.  No shared memory involved (the
+// shared-memory port is the tensor core's operand path).
+__device__ __forceinline__ float warp_colsum32(float (&f)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? f[i] : f[i + off];
+      const float keep = upper ? f[i + off] : f[i];
+      f[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return f[0];
+}
+
 }  // namespace clk

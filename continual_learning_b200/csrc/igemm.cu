@@ -298,18 +298,11 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
           }
         }
         if (do_stats) {
-          // 32x32 transpose through shared memory: lane j then owns column (chunk*32 + j)
-          __syncwarp();
+          float fq[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) scratch[lane * 33 + j] = f[j];
-          __syncwarp();
-          float s = 0.f, sq = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = scratch[i * 33 + lane];
-            s += x;
-            sq = fmaf(x, x, sq);
-          }
+          for (int j = 0; j < 32; ++j) fq[j] = f[j] * f[j];
+          const float s = warp_colsum32(f, lane);
+          const float sq = warp_colsum32(fq, lane);
           atomicAdd(&s_sum[chunk * 32 + lane], s);
           atomicAdd(&s_sq[chunk * 32 + lane], sq);
         }
@@ -843,7 +836,7 @@ __global__ void __launch_bounds__(kC3Threads, 1)
       mbar_wait(&acc_full[acc], pacc);
       tc_fence_after();
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int chunk = 0; chunk < (p.relu == 77 ? 0 : BN / 32); ++chunk) {  // relu == 77: debug, main loop only
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 2 * BN + j * BN + chunk * 32, v);
         tmem_ld_wait();
@@ -874,20 +867,18 @@ __global__ void __launch_bounds__(kC3Threads, 1)
             o[jj] = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
         }
         if (do_stats) {
-          __syncwarp();
+          // statistics of the values exactly as stored (bf16-rounded), reduced over the 32 rows with shuffles
+          float fs[32], fq[32];
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
-            scratch[lane * 33 + 2 * jj] = valid ? bf16lo_to_f32(pk[jj]) : 0.f;
-            scratch[lane * 33 + 2 * jj + 1] = valid ? bf16hi_to_f32(pk[jj]) : 0.f;
+            const float lo = valid ? bf16lo_to_f32(pk[jj]) : 0.f, hi = valid ? bf16hi_to_f32(pk[jj]) : 0.f;
+            fs[2 * jj] = lo;
+            fs[2 * jj + 1] = hi;
+            fq[2 * jj] = lo * lo;
+            fq[2 * jj + 1] = hi * hi;
           }
-          __syncwarp();
-          float s = 0.f, sq = 0.f;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = scratch[i * 33 + lane];
-            s += x;
-            sq = fmaf(x, x, sq);
-          }
+          const float s = warp_colsum32(fs, lane);
+          const float sq = warp_colsum32(fq, lane);
           atomicAdd(&s_sum[chunk * 32 + lane], s);
           atomicAdd(&s_sq[chunk * 32 + lane], sq);
         }
