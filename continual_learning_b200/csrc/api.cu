@@ -279,14 +279,16 @@ int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void
   if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (x1 == nullptr) != (C1 == 0))
     return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_fprop: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)",
                 C0, C1, Cout);
-  if (g_conv3_v2 && (H * W >= g_conv3_min_hw || g_conv3_v2 == 2)) {
+  if (g_conv3_v2 && (H * W >= g_conv3_min_hw || g_conv3_v2 == 2 || g_conv3_v2 == 4)) {
     Conv3Params q;
     memset(&q, 0, sizeof(q));
     q.N = N; q.H = H; q.W = W;
     q.tiles_w = (W + 15) / 16;
     q.tiles_h = (H + 15) / 16;
     q.m_tiles = N * q.tiles_h * q.tiles_w;
-    const int BNq = (Cout % 128 == 0 && g_fprop_bn != 64) ? 128 : 64;
+    const bool pair = g_conv3_v2 == 3 || g_conv3_v2 == 4;  // 3: pair kernel on large maps, 4: everywhere  // CTA-pair kernel (cta_group::2)
+    int BNq = (Cout % 128 == 0 && g_fprop_bn != 64) ? 128 : 64;
+    if (pair && Cout % 256 == 0 && g_fprop_bn != 64 && g_fprop_bn != 128) BNq = 256;
     q.n_tiles = Cout / BNq;
     q.kc0 = C0 / 64;
     q.kc1 = C1 / 64;
@@ -298,10 +300,12 @@ int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void
     q.stat_sum = stat_sum;
     q.stat_sq = stat_sq;
     CUtensorMap a0, a1, b;
-    CHECK_RC(map_nhwc(&a0, x0, N, H, W, C0, 24, 18, 1));
-    if (x1) CHECK_RC(map_nhwc(&a1, x1, N, H, W, C1, 24, 18, 1));
+    const int bw = pair ? 16 : 24;
+    CHECK_RC(map_nhwc(&a0, x0, N, H, W, C0, bw, 18, 1));
+    if (x1) CHECK_RC(map_nhwc(&a1, x1, N, H, W, C1, bw, 18, 1));
     else a1 = a0;
-    CHECK_RC(map_weights(&b, w, 9, Cout, C0 + C1, BNq));
+    CHECK_RC(map_weights(&b, w, 9, Cout, C0 + C1, pair ? BNq / 2 : BNq));
+    if (pair) return cuda_status(launch_conv3x2(BNq, a0, a1, b, q, g_num_sms_api, S(st)), "conv3x3_fprop(pair)");
     return cuda_status(launch_conv3(BNq, a0, a1, b, q, g_num_sms_api, S(st)), "conv3x3_fprop(halo)");
   }
   FpropParams p;
@@ -332,7 +336,7 @@ int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C
   if (!dy || !wd || !dx0 || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "conv3x3_dgrad: bad args");
   if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (dx1 == nullptr) != (C1 == 0))
     return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_dgrad: channels must be multiples of 64");
-  if (g_conv3_v2 && (H * W >= g_conv3_min_hw || g_conv3_v2 == 2)) {
+  if (g_conv3_v2 && (H * W >= g_conv3_min_hw || g_conv3_v2 == 2 || g_conv3_v2 == 4)) {
     Conv3Params q;
     memset(&q, 0, sizeof(q));
     const int Cin2 = C0 + C1;
@@ -340,7 +344,9 @@ int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C
     q.tiles_w = (W + 15) / 16;
     q.tiles_h = (H + 15) / 16;
     q.m_tiles = N * q.tiles_h * q.tiles_w;
-    const int BNq = (Cin2 % 128 == 0 && g_fprop_bn != 64) ? 128 : 64;  // a tile may straddle the C0 | C1 split
+    const bool pair = g_conv3_v2 == 3 || g_conv3_v2 == 4;  // 3: pair kernel on large maps, 4: everywhere
+    int BNq = (Cin2 % 128 == 0 && g_fprop_bn != 64) ? 128 : 64;  // a tile may straddle the C0 | C1 split
+    if (pair && Cin2 % 256 == 0 && g_fprop_bn != 64 && g_fprop_bn != 128) BNq = 256;
     q.n_tiles = Cin2 / BNq;
     q.kc0 = Cout / 64;
     q.kc1 = 0;
@@ -351,8 +357,9 @@ int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C
     q.dst1 = dx1;
     q.ldc1 = C1;
     CUtensorMap a0, b;
-    CHECK_RC(map_nhwc(&a0, dy, N, H, W, Cout, 24, 18, 1));
-    CHECK_RC(map_weights(&b, wd, 9, Cin2, Cout, BNq));
+    CHECK_RC(map_nhwc(&a0, dy, N, H, W, Cout, pair ? 16 : 24, 18, 1));
+    CHECK_RC(map_weights(&b, wd, 9, Cin2, Cout, pair ? BNq / 2 : BNq));
+    if (pair) return cuda_status(launch_conv3x2(BNq, a0, a0, b, q, g_num_sms_api, S(st)), "conv3x3_dgrad(pair)");
     return cuda_status(launch_conv3(BNq, a0, a0, b, q, g_num_sms_api, S(st)), "conv3x3_dgrad(halo)");
   }
   FpropParams p;

@@ -931,6 +931,304 @@ cudaError_t launch_conv3(int BN, const CUtensorMap& a0, const CUtensorMap& a1, c
 }
 
 // ------------------------------------------------------------------------------------------
+// CONV3x2 (conv3x3 forward / dgrad, halo variant, CTA PAIRS: tcgen05.mma.cta_group::2, M = 256).
+//   A cluster of two CTAs owns one 16x16-pixel super tile; CTA r owns the 16x8 half r (its own halo tile,
+//   18 rows x 16 px, row pitch 2048 B) = 128 rows of the M=256 MMA and 128 lanes of accumulator in its own TMEM;
+//   the [BN][64] weight tile of a tap is split: each CTA loads BN/2 rows, the tensor cores of the pair share them.
+//   Per MMA and per SM the shared-memory port then moves A 4 KB + B BN*16 B instead of A 4 KB + B BN*32 B, and each
+//   weight byte is written to shared memory once per PAIR — the port, not the tensor pipe, limits the 1-CTA kernels.
+//   Leader (rank 0): issues all MMAs, owns the full barriers (both CTAs' TMA loads credit them) and the
+//   accumulator-empty barriers (16 arrivals: 8 epilogue warps of each CTA); empty / accumulator-full barriers live in
+//   both CTAs and are signalled by multicast tcgen05.commit.
+constexpr int kX2ABytes = 18 * 16 * 128;
+constexpr int kX2AStages = 3;
+template <int BN>
+struct X2Cfg {
+  static constexpr int NB = (BN == 256) ? 6 : 8;
+  static constexpr int BBytes = (BN / 2) * 128;
+  static constexpr int Smem = kX2AStages * kX2ABytes + NB * BBytes + 3 * BN * 4 + (2 * kX2AStages + 2 * NB + 4) * 8 + 16 + 1024;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
+    igemm_conv3x2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                         const __grid_constant__ CUtensorMap mapB, const __grid_constant__ Conv3Params p) {
+  constexpr int NB = X2Cfg<BN>::NB;
+  constexpr int B_BYTES = X2Cfg<BN>::BBytes;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr int AS = kX2AStages;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + AS * kX2ABytes;
+  float* s_sum = reinterpret_cast<float*>(sB + NB * B_BYTES);
+  float* s_sq = s_sum + BN;
+  float* s_bias = s_sq + BN;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_bias + BN);
+  uint64_t* a_empty = a_full + AS;
+  uint64_t* acc_full = a_empty + AS;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* b_full = acc_empty + 2;
+  uint64_t* b_empty = b_full + NB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_empty + NB);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int nclusters = gridDim.x >> 1;
+  const int kc = p.kc0 + p.kc1;
+  const int total = p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < AS; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 16);
+    }
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  for (int i = threadIdx.x; i < 3 * BN; i += kC3Threads) s_sum[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / cross-CTA TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (one per CTA)
+    if (elect_one()) {
+      uint32_t ia = 0, ib = 0;
+      int tA = cluster_id, chA = 0;
+      int tB = cluster_id, chB = 0, tapB = 0;
+      uint32_t idle = 0;
+      while (tB < total) {
+        if (++idle > CLK_SPIN_LIMIT) __trap();
+        if (tA < total && ia <= ib / 9 + (AS - 1)) {
+          const uint32_t sa = ia % AS, pa = (ia / AS) & 1;
+          if (mbar_try_wait(&a_empty[sa], pa ^ 1)) {
+            const int m = tA % p.m_tiles;
+            const int tx = m % p.tiles_w;
+            const int r = m / p.tiles_w;
+            const int ty = r % p.tiles_h;
+            const int n = r / p.tiles_h;
+            if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * kX2ABytes);
+            const int w0 = tx * 16 + 8 * static_cast<int>(rank) - 1;
+            if (chA < p.kc0)
+              tma_load_5d_2sm(sA + sa * kX2ABytes, &mapA0, leader_bar_addr(&a_full[sa]), chA * 64, w0, ty * 16 - 1, n, 0);
+            else
+              tma_load_5d_2sm(sA + sa * kX2ABytes, &mapA1, leader_bar_addr(&a_full[sa]), (chA - p.kc0) * 64, w0,
+                              ty * 16 - 1, n, 0);
+            ++ia;
+            idle = 0;
+            if (++chA == kc) {
+              chA = 0;
+              tA += nclusters;
+            }
+          }
+        }
+        {
+          const uint32_t sb = ib % NB, pb = (ib / NB) & 1;
+          if (mbar_try_wait(&b_empty[sb], pb ^ 1)) {
+            if (leader) mbar_arrive_expect_tx(&b_full[sb], 2 * B_BYTES);
+            tma_load_3d_2sm(sB + sb * B_BYTES, &mapB, leader_bar_addr(&b_full[sb]), chB * 64,
+                            (tB / p.m_tiles) * BN + static_cast<int>(rank) * (BN / 2), tapB);
+            ++ib;
+            idle = 0;
+            if (++tapB == 9) {
+              tapB = 0;
+              if (++chB == kc) {
+                chB = 0;
+                tB += nclusters;
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer: leader CTA only
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN, 0, 0);
+      uint32_t ia = 0, ib = 0, it = 0;
+      for (int t = cluster_id; t < total; t += nclusters, ++it) {
+        const uint32_t acc = it & 1, pacc = (it >> 1) & 1;
+        mbar_wait(&acc_empty[acc], pacc ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * BN;
+        for (int ch = 0; ch < kc; ++ch) {
+          const uint32_t sa = ia % AS, pa = (ia / AS) & 1;
+          mbar_wait(&a_full[sa], pa);
+          const uint32_t abase = smem_u32(sA + sa * kX2ABytes);
+#pragma unroll 1
+          for (int tr = 0; tr < 3; ++tr) {
+#pragma unroll 1
+            for (int tsx = 0; tsx < 3; ++tsx) {
+              const uint32_t sb = ib % NB, pb = (ib / NB) & 1;
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              const uint32_t a = abase + (tr * 16 + tsx) * 128;
+              const uint32_t b = smem_u32(sB + sb * B_BYTES);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16_2cta(d0, umma_smem_desc(a + k * 32, 16, 2048), umma_smem_desc(b + k * 32, 16, 1024), idesc,
+                               (ch | tr | tsx | k) != 0 ? 1u : 0u);
+              }
+              umma_commit_2cta(&b_empty[sb]);
+              ++ib;
+            }
+          }
+          umma_commit_2cta(&a_empty[sa]);
+          ++ia;
+        }
+        umma_commit_2cta(&acc_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------ epilogue (8 warps per CTA: quadrant = warp % 4, the two warps
+    // of a quadrant split the 32-column chunks)
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int mrow = q * 32 + lane;
+    const int etid = threadIdx.x - 64;
+    const bool do_stats = p.stat_sum != nullptr;
+    uint32_t it = 0;
+    int bias_nt = -1;
+    for (int t = cluster_id; t < total; t += nclusters, ++it) {
+      const int m = t % p.m_tiles, nt = t / p.m_tiles;
+      const int tx = m % p.tiles_w;
+      const int r = m / p.tiles_w;
+      const int ty = r % p.tiles_h;
+      const int n = r / p.tiles_h;
+      const int n0 = nt * BN;
+      const uint32_t acc = it & 1, pacc = (it >> 1) & 1;
+      if (nt != bias_nt) {
+        named_bar_sync(2, kC3EpiThreads);
+        for (int i = etid; i < BN; i += kC3EpiThreads)
+          s_bias[i] = (p.bias != nullptr && n0 + i < p.n_store) ? p.bias[n0 + i] : 0.f;
+        named_bar_sync(2, kC3EpiThreads);
+        bias_nt = nt;
+      }
+      const int h = ty * 16 + (mrow >> 3);
+      const int w = tx * 16 + 8 * static_cast<int>(rank) + (mrow & 7);
+      const bool valid = h < p.H && w < p.W;
+      const long long pixoff = valid ? (static_cast<long long>(n) * p.H + h) * p.W + w : 0;
+      mbar_wait(&acc_full[acc], pacc);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = half; chunk < BN / 32; chunk += 2) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, v);
+        tmem_ld_wait();
+        const bool in_store = (n0 + chunk * 32) < p.n_store;
+        uint32_t pk[16];
+        const float4* b4 = reinterpret_cast<const float4*>(s_bias + chunk * 32);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const float4 bb = b4[jj];
+          float x0 = __uint_as_float(v[4 * jj]) + bb.x, x1 = __uint_as_float(v[4 * jj + 1]) + bb.y;
+          float x2 = __uint_as_float(v[4 * jj + 2]) + bb.z, x3 = __uint_as_float(v[4 * jj + 3]) + bb.w;
+          if (p.relu) {
+            x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+          }
+          pk[2 * jj] = pack_bf16x2(x0, x1);
+          pk[2 * jj + 1] = pack_bf16x2(x2, x3);
+        }
+        if (valid && in_store) {
+          const int gc = n0 + chunk * 32;
+          __nv_bfloat16* orow = (p.split_c > 0 && gc >= p.split_c)
+                                    ? reinterpret_cast<__nv_bfloat16*>(p.dst1) + pixoff * p.ldc1 + (gc - p.split_c)
+                                    : reinterpret_cast<__nv_bfloat16*>(p.dst0) + pixoff * p.ldc0 + gc;
+          uint4* o = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj)
+            o[jj] = make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+        }
+        if (do_stats) {
+          float fs[32], fq[32];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const float lo = valid ? bf16lo_to_f32(pk[jj]) : 0.f, hi = valid ? bf16hi_to_f32(pk[jj]) : 0.f;
+            fs[2 * jj] = lo;
+            fs[2 * jj + 1] = hi;
+            fq[2 * jj] = lo * lo;
+            fq[2 * jj + 1] = hi * hi;
+          }
+          const float s = warp_colsum32(fs, lane);
+          const float sq = warp_colsum32(fq, lane);
+          atomicAdd(&s_sum[chunk * 32 + lane], s);
+          atomicAdd(&s_sq[chunk * 32 + lane], sq);
+        }
+      }
+      // this warp is done with the accumulator stage: tell the leader's MMA thread (16 arrivals free the stage)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
+      if (do_stats) {
+        named_bar_sync(1, kC3EpiThreads);
+        for (int i = etid; i < BN; i += kC3EpiThreads) {
+          if (n0 + i < p.n_store) {
+            atomicAdd(&p.stat_sum[n0 + i], static_cast<double>(s_sum[i]));
+            atomicAdd(&p.stat_sq[n0 + i], static_cast<double>(s_sq[i]));
+          }
+          s_sum[i] = 0.f;
+          s_sq[i] = 0.f;
+        }
+        named_bar_sync(1, kC3EpiThreads);
+      }
+    }
+  }
+
+  // the leader's MMAs read the peer's shared memory and write its TMEM: nobody leaves before everybody is done
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+}
+
+template <int BN>
+static cudaError_t launch_conv3x2_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                                    const Conv3Params& p, int num_sms, cudaStream_t st) {
+  constexpr int smem = X2Cfg<BN>::Smem;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_conv3x2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  int clusters = p.m_tiles * p.n_tiles;
+  if (clusters > num_sms / 2) clusters = num_sms / 2;
+  igemm_conv3x2_kernel<BN><<<2 * clusters, kC3Threads, smem, st>>>(a0, a1, b, p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_conv3x2(int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+                           const Conv3Params& p, int num_sms, cudaStream_t st) {
+  if (BN == 256) return launch_conv3x2_t<256>(a0, a1, b, p, num_sms, st);
+  if (BN == 128) return launch_conv3x2_t<128>(a0, a1, b, p, num_sms, st);
+  if (BN == 64) return launch_conv3x2_t<64>(a0, a1, b, p, num_sms, st);
+  return cudaErrorInvalidValue;
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 template <int BN, int STAGES>
 static constexpr int fprop_smem_bytes() {
