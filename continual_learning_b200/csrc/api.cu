@@ -20,6 +20,7 @@ int g_wgrad_ksplit = 0;
 int g_wgrad_bn = 64;
 int g_wgrad_v2 = 1;
 int g_conv3_v2 = 1;
+int g_conv3_pair = 1;        // CTA-pair kernel (cta_group::2, BN = 256) whenever the N extent is a multiple of 256
 int g_conv3_min_hw = 2048;  // halo kernel for images with at least this many pixels; smaller maps use the generic kernel (BN up to 256)
 int g_num_sms_api = 148;
 
@@ -228,6 +229,7 @@ int clk_set_tuning(const char* key, int value) {
   else if (strcmp(key, "wgrad_v2") == 0) g_wgrad_v2 = value;
   else if (strcmp(key, "conv3_v2") == 0) g_conv3_v2 = value;
   else if (strcmp(key, "conv3_min_hw") == 0) g_conv3_min_hw = value;
+  else if (strcmp(key, "conv3_pair") == 0) g_conv3_pair = value;
   else return fail(CLK_E_BADARG, "unknown tuning key %s", key);
   return CLK_OK;
 }
@@ -279,14 +281,15 @@ int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void
   if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (x1 == nullptr) != (C1 == 0))
     return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_fprop: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)",
                 C0, C1, Cout);
-  if (g_conv3_v2 && (H * W >= g_conv3_min_hw || g_conv3_v2 == 2 || g_conv3_v2 == 4)) {
+  const bool pair_f = g_conv3_v2 == 4 || (g_conv3_v2 && g_conv3_pair && Cout % 256 == 0 && g_fprop_bn == 0);
+  if (pair_f || (g_conv3_v2 && (H * W >= g_conv3_min_hw || g_conv3_v2 == 2))) {
     Conv3Params q;
     memset(&q, 0, sizeof(q));
     q.N = N; q.H = H; q.W = W;
     q.tiles_w = (W + 15) / 16;
     q.tiles_h = (H + 15) / 16;
     q.m_tiles = N * q.tiles_h * q.tiles_w;
-    const bool pair = g_conv3_v2 == 3 || g_conv3_v2 == 4;  // 3: pair kernel on large maps, 4: everywhere  // CTA-pair kernel (cta_group::2)
+    const bool pair = pair_f;  // CTA-pair kernel (cta_group::2)
     int BNq = (Cout % 128 == 0 && g_fprop_bn != 64) ? 128 : 64;
     if (pair && Cout % 256 == 0 && g_fprop_bn != 64 && g_fprop_bn != 128) BNq = 256;
     q.n_tiles = Cout / BNq;
@@ -336,7 +339,8 @@ int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C
   if (!dy || !wd || !dx0 || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "conv3x3_dgrad: bad args");
   if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (dx1 == nullptr) != (C1 == 0))
     return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_dgrad: channels must be multiples of 64");
-  if (g_conv3_v2 && (H * W >= g_conv3_min_hw || g_conv3_v2 == 2 || g_conv3_v2 == 4)) {
+  const bool pair_d = g_conv3_v2 == 4 || (g_conv3_v2 && g_conv3_pair && (C0 + C1) % 256 == 0 && g_fprop_bn == 0);
+  if (pair_d || (g_conv3_v2 && (H * W >= g_conv3_min_hw || g_conv3_v2 == 2))) {
     Conv3Params q;
     memset(&q, 0, sizeof(q));
     const int Cin2 = C0 + C1;
@@ -344,7 +348,7 @@ int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C
     q.tiles_w = (W + 15) / 16;
     q.tiles_h = (H + 15) / 16;
     q.m_tiles = N * q.tiles_h * q.tiles_w;
-    const bool pair = g_conv3_v2 == 3 || g_conv3_v2 == 4;  // 3: pair kernel on large maps, 4: everywhere
+    const bool pair = pair_d;
     int BNq = (Cin2 % 128 == 0 && g_fprop_bn != 64) ? 128 : 64;  // a tile may straddle the C0 | C1 split
     if (pair && Cin2 % 256 == 0 && g_fprop_bn != 64 && g_fprop_bn != 128) BNq = 256;
     q.n_tiles = Cin2 / BNq;

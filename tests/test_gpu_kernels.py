@@ -62,14 +62,17 @@ def test_gemm_fprop_bias_relu_stats(ops, P, K, N):
     assert rel(s_sum, q.sum(0)) <= 1e-6 and rel(s_sq, (q * q).sum(0)) <= 1e-6
 
 
-@pytest.fixture(params=["generic", "halo"])
+@pytest.fixture(params=["generic", "halo", "pair"])
 def conv_kernel(request):
-    """run the conv3x3 forward/dgrad cases through both tcgen05 kernels: the generic per-tap-TMA kernel and the
-    persistent halo kernel (the library picks between them by image size; the knob forces one)."""
+    """run the conv3x3 forward/dgrad cases through all three tcgen05 kernels: the generic per-tap-TMA kernel, the
+    persistent halo kernel and the CTA-pair (cta_group::2, M = 256) halo kernel.  The library picks between them by
+    image size and channel count; the knobs force one."""
     from continual_learning_b200 import _lib
-    _lib.set_tuning("conv3_v2", 2 if request.param == "halo" else 0)
+    _lib.set_tuning("conv3_v2", {"generic": 0, "halo": 2, "pair": 4}[request.param])
+    _lib.set_tuning("conv3_pair", 0 if request.param == "halo" else 1)
     yield request.param
     _lib.set_tuning("conv3_v2", 1)
+    _lib.set_tuning("conv3_pair", 1)
 
 
 @pytest.mark.parametrize("n,h,w,c0,c1,co", [(2, 16, 16, 64, 0, 64), (3, 8, 24, 128, 0, 256), (2, 16, 16, 64, 64, 128),
