@@ -303,7 +303,11 @@ int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void
     q.stat_sum = stat_sum;
     q.stat_sq = stat_sq;
     CUtensorMap a0, a1, b;
-    const int bw = pair ? 16 : 24;
+    const int bw = (pair && BNq == 256) ? 16 : 24;
+    if (pair && BNq != 256) {  // two sub tiles per CTA: the pair covers 16 x 32 pixels
+      q.tiles_w = (W + 31) / 32;
+      q.m_tiles = N * q.tiles_h * q.tiles_w;
+    }
     CHECK_RC(map_nhwc(&a0, x0, N, H, W, C0, bw, 18, 1));
     if (x1) CHECK_RC(map_nhwc(&a1, x1, N, H, W, C1, bw, 18, 1));
     else a1 = a0;
@@ -361,7 +365,11 @@ int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C
     q.dst1 = dx1;
     q.ldc1 = C1;
     CUtensorMap a0, b;
-    CHECK_RC(map_nhwc(&a0, dy, N, H, W, Cout, pair ? 16 : 24, 18, 1));
+    if (pair && BNq != 256) {
+      q.tiles_w = (W + 31) / 32;
+      q.m_tiles = N * q.tiles_h * q.tiles_w;
+    }
+    CHECK_RC(map_nhwc(&a0, dy, N, H, W, Cout, (pair && BNq == 256) ? 16 : 24, 18, 1));
     CHECK_RC(map_weights(&b, wd, 9, Cin2, Cout, pair ? BNq / 2 : BNq));
     if (pair) return cuda_status(launch_conv3x2(BNq, a0, a0, b, q, g_num_sms_api, S(st)), "conv3x3_dgrad(pair)");
     return cuda_status(launch_conv3(BNq, a0, a0, b, q, g_num_sms_api, S(st)), "conv3x3_dgrad(halo)");

@@ -940,23 +940,30 @@ cudaError_t launch_conv3(int BN, const CUtensorMap& a0, const CUtensorMap& a1, c
 //   Leader (rank 0): issues all MMAs, owns the full barriers (both CTAs' TMA loads credit them) and the
 //   accumulator-empty barriers (16 arrivals: 8 epilogue warps of each CTA); empty / accumulator-full barriers live in
 //   both CTAs and are signalled by multicast tcgen05.commit.
-constexpr int kX2ABytes = 18 * 16 * 128;
-constexpr int kX2AStages = 3;
-template <int BN>
+// SUB = number of 16x8 sub tiles per CTA: 1 for BN = 256 (the pair covers 16x16 pixels), 2 for BN <= 128 (the pair
+// covers 16x32 pixels, every weight tile then feeds four M=128 row blocks).
+template <int BN, int SUB>
 struct X2Cfg {
-  static constexpr int NB = (BN == 256) ? 6 : 8;
+  static constexpr int PitchPx = SUB == 1 ? 16 : 24;           // halo row pitch in pixels (box width)
+  static constexpr int ABytes = 18 * PitchPx * 128;
+  static constexpr int AS = SUB == 1 ? 3 : 2;                  // halo stages
+  static constexpr int NB = (BN == 256) ? 6 : 8;               // weight stages
   static constexpr int BBytes = (BN / 2) * 128;
-  static constexpr int Smem = kX2AStages * kX2ABytes + NB * BBytes + 3 * BN * 4 + (2 * kX2AStages + 2 * NB + 4) * 8 + 16 + 1024;
+  static constexpr int Smem = AS * ABytes + NB * BBytes + 3 * BN * 4 + (2 * AS + 2 * NB + 4) * 8 + 16 + 1024;
 };
 
-template <int BN>
+template <int BN, int SUB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
     igemm_conv3x2_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
                          const __grid_constant__ CUtensorMap mapB, const __grid_constant__ Conv3Params p) {
-  constexpr int NB = X2Cfg<BN>::NB;
-  constexpr int B_BYTES = X2Cfg<BN>::BBytes;
-  constexpr uint32_t TMEM_COLS = 2 * BN;
-  constexpr int AS = kX2AStages;
+  using Cfg = X2Cfg<BN, SUB>;
+  constexpr int NB = Cfg::NB;
+  constexpr int B_BYTES = Cfg::BBytes;
+  constexpr uint32_t TMEM_COLS = 2 * SUB * BN;
+  constexpr int AS = Cfg::AS;
+  constexpr int kX2ABytes = Cfg::ABytes;
+  constexpr int PITCH = Cfg::PitchPx;       // pixels
+  constexpr int TILE_W = 8 * SUB;           // output columns owned by one CTA
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -1029,7 +1036,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
             const int ty = r % p.tiles_h;
             const int n = r / p.tiles_h;
             if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * kX2ABytes);
-            const int w0 = tx * 16 + 8 * static_cast<int>(rank) - 1;
+            const int w0 = tx * (2 * TILE_W) + TILE_W * static_cast<int>(rank) - 1;
             if (chA < p.kc0)
               tma_load_5d_2sm(sA + sa * kX2ABytes, &mapA0, leader_bar_addr(&a_full[sa]), chA * 64, w0, ty * 16 - 1, n, 0);
             else
@@ -1072,7 +1079,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
         const uint32_t acc = it & 1, pacc = (it >> 1) & 1;
         mbar_wait(&acc_empty[acc], pacc ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * BN;
+        const uint32_t d0 = tmem_base + acc * SUB * BN;
         for (int ch = 0; ch < kc; ++ch) {
           const uint32_t sa = ia % AS, pa = (ia / AS) & 1;
           mbar_wait(&a_full[sa], pa);
@@ -1084,12 +1091,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
               const uint32_t sb = ib % NB, pb = (ib / NB) & 1;
               mbar_wait(&b_full[sb], pb);
               tc_fence_after();
-              const uint32_t a = abase + (tr * 16 + tsx) * 128;
+              const uint32_t a = abase + (tr * PITCH + tsx) * 128;
               const uint32_t b = smem_u32(sB + sb * B_BYTES);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16_2cta(d0, umma_smem_desc(a + k * 32, 16, 2048), umma_smem_desc(b + k * 32, 16, 1024), idesc,
-                               (ch | tr | tsx | k) != 0 ? 1u : 0u);
+              for (int j = 0; j < SUB; ++j) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16_2cta(d0 + j * BN, umma_smem_desc(a + j * 1024 + k * 32, 16, PITCH * 128),
+                                 umma_smem_desc(b + k * 32, 16, 1024), idesc, (ch | tr | tsx | k) != 0 ? 1u : 0u);
+                }
               }
               umma_commit_2cta(&b_empty[sb]);
               ++ib;
@@ -1107,6 +1117,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
     // of a quadrant split the 32-column chunks)
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
+    // SUB == 1: the two warps of a quadrant split the column chunks; SUB == 2: they take one sub tile each
+    const int j = SUB == 2 ? half : 0;
+    const int chunk0 = SUB == 2 ? 0 : half;
+    const int chunk_step = SUB == 2 ? 1 : 2;
     const int mrow = q * 32 + lane;
     const int etid = threadIdx.x - 64;
     const bool do_stats = p.stat_sum != nullptr;
@@ -1128,15 +1142,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
         bias_nt = nt;
       }
       const int h = ty * 16 + (mrow >> 3);
-      const int w = tx * 16 + 8 * static_cast<int>(rank) + (mrow & 7);
+      const int w = tx * (2 * TILE_W) + TILE_W * static_cast<int>(rank) + j * 8 + (mrow & 7);
       const bool valid = h < p.H && w < p.W;
       const long long pixoff = valid ? (static_cast<long long>(n) * p.H + h) * p.W + w : 0;
       mbar_wait(&acc_full[acc], pacc);
       tc_fence_after();
 #pragma unroll 1
-      for (int chunk = half; chunk < BN / 32; chunk += 2) {
+      for (int chunk = chunk0; chunk < BN / 32; chunk += chunk_step) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + chunk * 32, v);
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * SUB * BN + j * BN + chunk * 32, v);
         tmem_ld_wait();
         const bool in_store = (n0 + chunk * 32) < p.n_store;
         uint32_t pk[16];
@@ -1204,27 +1218,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
   if (warp == 1) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
 }
 
-template <int BN>
+template <int BN, int SUB>
 static cudaError_t launch_conv3x2_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                                     const Conv3Params& p, int num_sms, cudaStream_t st) {
-  constexpr int smem = X2Cfg<BN>::Smem;
+  constexpr int smem = X2Cfg<BN, SUB>::Smem;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_conv3x2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(igemm_conv3x2_kernel<BN, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   int clusters = p.m_tiles * p.n_tiles;
   if (clusters > num_sms / 2) clusters = num_sms / 2;
-  igemm_conv3x2_kernel<BN><<<2 * clusters, kC3Threads, smem, st>>>(a0, a1, b, p);
+  igemm_conv3x2_kernel<BN, SUB><<<2 * clusters, kC3Threads, smem, st>>>(a0, a1, b, p);
   return cudaGetLastError();
 }
 
+// BN = 256: one sub tile per CTA (a0/a1 box {64, 16, 18}, tiles of 16x16 px per pair);
+// BN = 128 / 64: two sub tiles per CTA (box {64, 24, 18}, tiles of 16x32 px per pair).  b box {64, BN/2, 1}.
 cudaError_t launch_conv3x2(int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const Conv3Params& p, int num_sms, cudaStream_t st) {
-  if (BN == 256) return launch_conv3x2_t<256>(a0, a1, b, p, num_sms, st);
-  if (BN == 128) return launch_conv3x2_t<128>(a0, a1, b, p, num_sms, st);
-  if (BN == 64) return launch_conv3x2_t<64>(a0, a1, b, p, num_sms, st);
+  if (BN == 256) return launch_conv3x2_t<256, 1>(a0, a1, b, p, num_sms, st);
+  if (BN == 128) return launch_conv3x2_t<128, 2>(a0, a1, b, p, num_sms, st);
+  if (BN == 64) return launch_conv3x2_t<64, 2>(a0, a1, b, p, num_sms, st);
   return cudaErrorInvalidValue;
 }
 
