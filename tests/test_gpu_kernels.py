@@ -71,7 +71,7 @@ def conv_kernel(request):
     _lib.set_tuning("conv3_v2", {"generic": 0, "halo": 2, "pair": 4}[request.param])
     _lib.set_tuning("conv3_pair", 0 if request.param == "halo" else 1)
     yield request.param
-    _lib.set_tuning("conv3_v2", 1)
+    _lib.set_tuning("conv3_v2", 4)
     _lib.set_tuning("conv3_pair", 1)
 
 
