@@ -417,8 +417,10 @@ int clk_conv3x3_wgrad(const void* dy, int Cout, const void* x0, int C0, const vo
     q.Cin = C0 + C1;
     q.Cout = Cout;
     q.out = dw;
+    const bool pair = g_wgrad_v2 == 2 && Cout % 128 == 0;  // CTA-pair kernel (cta_group::2)
+    if (pair) q.cout_tiles = Cout / 128;
     const int base = q.cin_slabs * q.cout_tiles;
-    int ks = g_wgrad_ksplit > 0 ? g_wgrad_ksplit : (g_num_sms_api / base);
+    int ks = g_wgrad_ksplit > 0 ? g_wgrad_ksplit : ((pair ? g_num_sms_api / 2 : g_num_sms_api) / base);
     if (ks < 1) ks = 1;
     if (ks > q.tiles_total) ks = q.tiles_total;
     q.ksplit = ks;
@@ -427,6 +429,7 @@ int clk_conv3x3_wgrad(const void* dy, int Cout, const void* x0, int C0, const vo
     CHECK_RC(map_nhwc(&t0, x0, N, H, W, C0, 16, 18, 1));
     if (x1) CHECK_RC(map_nhwc(&t1, x1, N, H, W, C1, 16, 18, 1));
     else t1 = t0;
+    if (pair) return cuda_status(launch_wgrad9x2(u, t0, t1, q, S(st)), "conv3x3_wgrad(pair)");
     return cuda_status(launch_wgrad9(u, t0, t1, q, S(st)), "conv3x3_wgrad(halo)");
   }
   WgradParams p;

@@ -635,6 +635,160 @@ cudaError_t launch_wgrad9(const CUtensorMap& u, const CUtensorMap& t0, const CUt
 }
 
 // ------------------------------------------------------------------------------------------
+// WGRAD9x2 (conv3x3 weight gradient, CTA pairs, cta_group::2, M = 256, N = 128).
+//   A pair owns 64 input channels x 128 output channels x all nine taps.  Both CTAs load the SAME 64-channel X halo
+//   tile, but CTA 1 loads it shifted down by one image row, so one shared A descriptor (start offset, LBO) selects
+//   different taps in the two CTAs: three MMA groups x (2 CTAs x 2 row blocks) = 12 tap slots for the 9 taps:
+//       group 0: offset (0,0), LBO = 1 px   -> CTA0 taps (0,0) (0,1)   CTA1 taps (1,0) (1,1)
+//       group 1: offset (0,2), LBO = 2 rows -> CTA0 taps (0,2) (2,2)   CTA1 taps (1,2)  --
+//       group 2: offset (2,0), LBO = 1 px   -> CTA0 taps (2,0) (2,1)   CTA1  --  --
+//   The dY tile (B operand, MN-major, N = 128) is split 64 + 64 channels between the CTAs.  Per MMA and SM the
+//   shared-memory port moves 6 KB per 64 cycles instead of 6 KB per 32 cycles in the 1-CTA kernel.
+constexpr int kW2Stages = 4;
+constexpr int kW2StageBytes = kW9UBytes + kW9TBytes;  // [128 px][64 cout] + [18 rows][16 px][64 cin]
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    igemm_wgrad9x2_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT0,
+                          const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ Wgrad9Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  // 2 KB pad after the last stage: CTA 1's unused tap slots read one halo row past their tile
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kW2Stages * kW2StageBytes + 2048);
+  uint64_t* empty = full + kW2Stages;
+  uint64_t* tmem_full = empty + kW2Stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cl = blockIdx.x >> 1;                 // cluster index within the (x) grid
+  const int co_tile = cl % p.cout_tiles;          // 128-channel tiles of dY
+  const int ci_slab = cl / p.cout_tiles;
+  const int per = (p.tiles_total + p.ksplit - 1) / p.ksplit;
+  const int t_begin = blockIdx.y * per;
+  const int num_kb = min(p.tiles_total, t_begin + per) - t_begin;
+  if (num_kb <= 0) return;  // uniform over the pair (same blockIdx.y)
+  constexpr uint32_t TMEM_COLS = 512;  // 3 groups x 128 columns
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kW2Stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&mapU);
+    tma_prefetch_desc(&mapT0);
+    tma_prefetch_desc(&mapT1);
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const bool src0 = ci_slab < p.split_slabs;
+      const CUtensorMap* mapT = src0 ? &mapT0 : &mapT1;
+      const int ct = (src0 ? ci_slab : ci_slab - p.split_slabs) * 64;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kW2Stages;
+        const uint32_t ph = (kb / kW2Stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (leader) mbar_arrive_expect_tx(&full[s], 2 * kW2StageBytes);
+        const int tile = t_begin + kb;
+        const int tx = tile % p.tiles_w;
+        const int r = tile / p.tiles_w;
+        const int ty = r % p.tiles_h;
+        const int n = r / p.tiles_h;
+        uint8_t* sU = smem + s * kW2StageBytes;
+        const uint32_t lbar = leader_bar_addr(&full[s]);
+        tma_load_5d_2sm(sU, &mapU, lbar, co_tile * 128 + 64 * static_cast<int>(rank), tx * 8, ty * 16, n, 0);
+        tma_load_5d_2sm(sU + kW9UBytes, mapT, lbar, ct, tx * 8 - 1, ty * 16 - 1 + static_cast<int>(rank), n, 0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, 128, 1, 1);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % kW2Stages;
+        const uint32_t ph = (kb / kW2Stages) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t u = smem_u32(smem + s * kW2StageBytes);
+        const uint32_t t = u + kW9UBytes;
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          const uint32_t offa = g == 0 ? 0u : (g == 1 ? 2u * 128u : 2u * 2048u);
+          const uint32_t lbo = g == 1 ? 2u * 2048u : 128u;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            umma_bf16_2cta(tmem_base + g * 128, umma_smem_desc(t + offa + k * 4096, lbo, 2048),
+                           umma_smem_desc(u + k * 2048, 8192, 1024), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+        }
+        umma_commit_2cta(&empty[s]);
+      }
+      umma_commit_2cta(tmem_full);
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int slot = row >> 6;
+    const int ci = ci_slab * 64 + (row & 63);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int g = 0; g < 3; ++g) {
+      // tap owned by (rank, group, slot); -1 = unused slot
+      int tap;
+      if (rank == 0) tap = g == 0 ? slot : (g == 1 ? (slot == 0 ? 2 : 8) : 6 + slot);
+      else tap = g == 0 ? 3 + slot : (g == 1 && slot == 0 ? 5 : -1);
+      float* obase = p.out + (static_cast<size_t>(tap < 0 ? 0 : tap) * p.Cin + ci) * p.Cout + co_tile * 128;
+#pragma unroll 1
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 128 + chunk * 32, v);
+        tmem_ld_wait();
+        if (tap >= 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            red_add_v4(obase + chunk * 32 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+}
+
+cudaError_t launch_wgrad9x2(const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
+                            const Wgrad9Params& p, cudaStream_t st) {
+  const int smem = kW2Stages * kW2StageBytes + 2048 + (2 * kW2Stages + 1) * 8 + 16 + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_wgrad9x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  dim3 grid(2 * p.cin_slabs * p.cout_tiles, p.ksplit);  // cout_tiles = Cout / 128 here
+  igemm_wgrad9x2_kernel<<<grid, kThreads, smem, st>>>(u, t0, t1, p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // CONV3 (conv3x3 forward / dgrad, halo variant, persistent).
 //   super tile = 16 x 16 output pixels of one image = two M=128 sub tiles (columns 0-7 / 8-15);
 //   A ring (2 stages): one [18 rows][24 px][64 ch] halo tile per 64-channel K chunk (row pitch 3072 B);

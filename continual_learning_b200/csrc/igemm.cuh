@@ -86,6 +86,9 @@ struct Wgrad9Params {
   int Cin, Cout;
   float* out;                         // [9][Cin][Cout] fp32, red.add accumulated (caller zeroes)
 };
+// CTA-pair variant (Cout % 128 == 0): p.cout_tiles counts 128-channel tiles
+cudaError_t launch_wgrad9x2(const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
+                            const Wgrad9Params& p, cudaStream_t st);
 cudaError_t launch_wgrad9(const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
                           const Wgrad9Params& p, cudaStream_t st);
 
