@@ -38,6 +38,7 @@ SIGNATURES = {
     "clk_conv3x3_fprop": [p, i, p, i, p, p, p, p, p, i, i, i, i, i, p],
     "clk_conv3x3_dgrad": [p, i, p, p, i, p, i, i, i, i, p],
     "clk_conv3x3_wgrad": [p, i, p, i, p, i, p, i, i, i, p],
+    "clk_conv3x3_wgrad_split": [p, i, p, i, p, i, p, i, i, i, p],
     "clk_gemm_fprop": [p, i, p, p, p, i, i, i, i, p, p, ll, i, p],
     "clk_gemm_wgrad": [p, i, p, i, p, i, i, ll, p],
     "clk_convT2x2_fprop": [p, p, p, p, i, i, i, i, i, p],
@@ -66,6 +67,7 @@ PLAIN = {
     "clk_last_error": ([], C.c_char_p),
     "clk_query_device": ([i], i),
     "clk_set_tuning": ([C.c_char_p, i], i),
+    "clk_conv3x3_wgrad_splits": ([i, i, i, i, i], i),
 }
 
 _lib = None

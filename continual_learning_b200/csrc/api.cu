@@ -398,32 +398,70 @@ int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C
   return cuda_status(launch_fprop(BN, 0, a0, a0, b, p, num_tiles(p.g), Cin / BN, S(st)), "conv3x3_dgrad");
 }
 
+static int wgrad9_plan(int Cout, int Cin, int N, int H, int W, Wgrad9Params& q, bool& pair) {
+  memset(&q, 0, sizeof(q));
+  q.N = N; q.H = H; q.W = W;
+  q.tiles_w = (W + 7) / 8;
+  q.tiles_h = (H + 15) / 16;
+  q.tiles_total = N * q.tiles_h * q.tiles_w;
+  q.cin_slabs = Cin / 64;
+  q.cout_tiles = Cout / 64;
+  q.Cin = Cin;
+  q.Cout = Cout;
+  pair = g_wgrad_v2 == 2 && Cout % 128 == 0;  // CTA-pair kernel (cta_group::2)
+  if (pair) q.cout_tiles = Cout / 128;
+  const int base = q.cin_slabs * q.cout_tiles;
+  int ks = g_wgrad_ksplit > 0 ? g_wgrad_ksplit : ((pair ? g_num_sms_api / 2 : g_num_sms_api) / base);
+  if (ks < 1) ks = 1;
+  if (ks > q.tiles_total) ks = q.tiles_total;
+  const int per = (q.tiles_total + ks - 1) / ks;
+  q.ksplit = (q.tiles_total + per - 1) / per;  // every split owns at least one pixel tile
+  return q.ksplit;
+}
+
+int clk_conv3x3_wgrad_splits(int Cout, int Cin, int N, int H, int W) {
+  if (Cout % 64 || Cin % 64 || Cout <= 0 || Cin <= 0 || N <= 0 || H <= 0 || W <= 0)
+    return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_wgrad_splits: channels must be multiples of 64");
+  if (!g_wgrad_v2) return 1;
+  Wgrad9Params q;
+  bool pair;
+  return wgrad9_plan(Cout, Cin, N, H, W, q, pair);
+}
+
+int clk_conv3x3_wgrad_split(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* partials,
+                            int N, int H, int W, clk_stream_t st) {
+  if (!dy || !x0 || !partials || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "conv3x3_wgrad_split: bad args");
+  if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (x1 == nullptr) != (C1 == 0))
+    return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_wgrad_split: channels must be multiples of 64");
+  if (!g_wgrad_v2) return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_wgrad_split needs the halo kernels (wgrad_v2 != 0)");
+  Wgrad9Params q;
+  bool pair;
+  wgrad9_plan(Cout, C0 + C1, N, H, W, q, pair);
+  q.split_slabs = C0 / 64;
+  q.out = partials;
+  q.split_stride = 9LL * (C0 + C1) * Cout;
+  CUtensorMap u, t0, t1;
+  CHECK_RC(map_nhwc(&u, dy, N, H, W, Cout, 8, 16, 1));
+  CHECK_RC(map_nhwc(&t0, x0, N, H, W, C0, 16, 18, 1));
+  if (x1) CHECK_RC(map_nhwc(&t1, x1, N, H, W, C1, 16, 18, 1));
+  else t1 = t0;
+  if (pair) return cuda_status(launch_wgrad9x2(u, t0, t1, q, S(st)), "conv3x3_wgrad_split(pair)");
+  return cuda_status(launch_wgrad9(u, t0, t1, q, S(st)), "conv3x3_wgrad_split(halo)");
+}
+
 int clk_conv3x3_wgrad(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw,
                       int N, int H, int W, clk_stream_t st) {
   if (!dy || !x0 || !dw || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "conv3x3_wgrad: bad args");
   if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (x1 == nullptr) != (C1 == 0))
     return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_wgrad: channels must be multiples of 64");
   if (g_wgrad_v2) {
-    // halo variant: (64 cin) x (64 cout) x 9 taps per CTA, 16x8-pixel K tiles
+    // halo variants: all nine taps per CTA (or CTA pair), 16x8-pixel K tiles, split-K accumulated with vector REDs
     Wgrad9Params q;
-    memset(&q, 0, sizeof(q));
-    q.N = N; q.H = H; q.W = W;
-    q.tiles_w = (W + 7) / 8;
-    q.tiles_h = (H + 15) / 16;
-    q.tiles_total = N * q.tiles_h * q.tiles_w;
-    q.cin_slabs = (C0 + C1) / 64;
+    bool pair;
+    wgrad9_plan(Cout, C0 + C1, N, H, W, q, pair);
     q.split_slabs = C0 / 64;
-    q.cout_tiles = Cout / 64;
-    q.Cin = C0 + C1;
-    q.Cout = Cout;
     q.out = dw;
-    const bool pair = g_wgrad_v2 == 2 && Cout % 128 == 0;  // CTA-pair kernel (cta_group::2)
-    if (pair) q.cout_tiles = Cout / 128;
-    const int base = q.cin_slabs * q.cout_tiles;
-    int ks = g_wgrad_ksplit > 0 ? g_wgrad_ksplit : ((pair ? g_num_sms_api / 2 : g_num_sms_api) / base);
-    if (ks < 1) ks = 1;
-    if (ks > q.tiles_total) ks = q.tiles_total;
-    q.ksplit = ks;
+    q.split_stride = 0;
     CUtensorMap u, t0, t1;
     CHECK_RC(map_nhwc(&u, dy, N, H, W, Cout, 8, 16, 1));
     CHECK_RC(map_nhwc(&t0, x0, N, H, W, C0, 16, 18, 1));

@@ -599,17 +599,24 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int pr = 0; pr < 5; ++pr) {
       const int tap = 2 * pr + (row >> 6);
       // packed gradient layout [tap][Cin][Cout]: this thread owns one (tap, ci) row -> 32 consecutive floats per chunk
-      float* obase = p.out + (static_cast<size_t>(tap) * p.Cin + ci) * p.Cout + co_tile * 64;
+      float* obase = p.out + static_cast<size_t>(blockIdx.y) * p.split_stride +
+                     (static_cast<size_t>(tap) * p.Cin + ci) * p.Cout + co_tile * 64;
 #pragma unroll 1
       for (int chunk = 0; chunk < 2; ++chunk) {
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + pr * 64 + chunk * 32, v);
         tmem_ld_wait();
         if (tap < 9) {
+          if (p.split_stride > 0) {  // this K split owns its own partial buffer: plain (deterministic) stores
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            red_add_v4(obase + chunk * 32 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(obase + chunk * 32 + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              red_add_v4(obase + chunk * 32 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          }
         }
       }
     }
@@ -752,17 +759,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       int tap;
       if (rank == 0) tap = g == 0 ? slot : (g == 1 ? (slot == 0 ? 2 : 8) : 6 + slot);
       else tap = g == 0 ? 3 + slot : (g == 1 && slot == 0 ? 5 : -1);
-      float* obase = p.out + (static_cast<size_t>(tap < 0 ? 0 : tap) * p.Cin + ci) * p.Cout + co_tile * 128;
+      float* obase = p.out + static_cast<size_t>(blockIdx.y) * p.split_stride +
+                     (static_cast<size_t>(tap < 0 ? 0 : tap) * p.Cin + ci) * p.Cout + co_tile * 128;
 #pragma unroll 1
       for (int chunk = 0; chunk < 4; ++chunk) {
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + g * 128 + chunk * 32, v);
         tmem_ld_wait();
         if (tap >= 0) {
+          if (p.split_stride > 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            red_add_v4(obase + chunk * 32 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<uint4*>(obase + chunk * 32 + 4 * j) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              red_add_v4(obase + chunk * 32 + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          }
         }
       }
     }

@@ -84,7 +84,9 @@ struct Wgrad9Params {
   int cout_tiles;                     // 64-channel tiles of dY
   int ksplit;
   int Cin, Cout;
-  float* out;                         // [9][Cin][Cout] fp32, red.add accumulated (caller zeroes)
+  float* out;                         // [9][Cin][Cout] fp32: red.add accumulated (caller zeroes) when split_stride == 0,
+                                      // else split s stores its partial sums at out + s*split_stride (no atomics)
+  long long split_stride;
 };
 // CTA-pair variant (Cout % 128 == 0): p.cout_tiles counts 128-channel tiles
 cudaError_t launch_wgrad9x2(const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,

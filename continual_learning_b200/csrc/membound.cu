@@ -1363,10 +1363,17 @@ __global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const long long
   const int na = min(32, A - a0), nb = min(32, B - b0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pitch = 32 * T + 1;
+  const int nsplit = static_cast<int>(J[12]) > 0 ? static_cast<int>(J[12]) : 1;  // split-K partial buffers to sum
+  const long long sstride = J[13];
   if (transposed) {
     for (int t = 0; t < T; ++t)
       for (int br = warp; br < nb; br += 8)
-        if (lane < na) tile[lane * pitch + br * T + t] = D[(static_cast<long long>(t) * ldB + b0 + br) * ldA + a0 + lane];
+        if (lane < na) {
+          const float* src = D + (static_cast<long long>(t) * ldB + b0 + br) * ldA + a0 + lane;
+          float v = 0.f;
+          for (int sp = 0; sp < nsplit; ++sp) v += src[sp * sstride];  // fixed order: deterministic
+          tile[lane * pitch + br * T + t] = v;
+        }
   } else {
     for (int t = 0; t < T; ++t)
       for (int ar = warp; ar < na; ar += 8)

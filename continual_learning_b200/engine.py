@@ -80,7 +80,7 @@ class UNetEngine:
         # packed fp32 weight-gradient accumulators + packed bf16 operand copies
         sizes = []
         for u in self.units:
-            sizes.append(64 * 64 if u.stem else 9 * u.cout * (u.c0 + u.c1))
+            sizes.append(64 * 64 if u.stem else 0)  # conv3x3 units write split-K partial buffers (see _ensure_wgrad_bufs)
         for (_, cm, co) in self.convT:
             sizes.append(4 * cm * co)
         sizes.append(64 * c_dim)
@@ -91,7 +91,8 @@ class UNetEngine:
             off += s
         nu = len(self.units)
         for i, u in enumerate(self.units):
-            u.gp = views[i].view(64, 64) if u.stem else views[i].view(9, u.c0 + u.c1, u.cout)
+            u.gp = views[i].view(64, 64) if u.stem else None
+            u.part, u.nsplit = None, 0
             if u.stem:
                 u.wf = torch.zeros((u.cout, 64), device=dev, dtype=bf16)
                 u.wd = None
@@ -127,15 +128,32 @@ class UNetEngine:
         self.hdbias = self.acc_b[ob:ob + 64]
         self._wver = None
         self._job_ptrs = None
+        self._wg_shape = None
+
+    def _ensure_wgrad_bufs(self, n, h, w):
+        """split-K partial buffers of the conv3x3 weight gradients: [nsplit][9][Cin][Cout] fp32 per layer; the number
+        of splits depends on the feature-map size (clk_conv3x3_wgrad_splits)."""
+        if self._wg_shape == (n, h, w):
+            return
+        self._wg_shape = (n, h, w)
+        down = [1, 1, 2, 2, 4, 4, 8, 8, 16, 16, 8, 8, 4, 4, 2, 2, 1, 1]
+        for u, d in zip(self.units, down):
+            if u.stem:
+                continue
+            cin = u.c0 + u.c1
+            u.nsplit = ops.conv3x3_wgrad_splits(u.cout, cin, n, h // d, w // d)
+            u.part = torch.empty((u.nsplit, 9, cin, u.cout), device=self._dev, dtype=f32)
+        self._job_ptrs = None  # the unpack table points at the partial buffers
 
     def _pack_weights(self):
+        ptrs = tuple(p.data_ptr() for p in self.params)
+        if ptrs != self._job_ptrs:  # parameters moved, or the split-K buffers were re-sized
+            self._build_jobs()
+            self._job_ptrs = ptrs
+            self._wver = None
         ver = (_lib.param_epoch,) + tuple(p._version for p in self.params) + tuple(p.data_ptr() for p in self.params[:2])
         if ver == self._wver:
             return
-        ptrs = tuple(p.data_ptr() for p in self.params)
-        if ptrs != self._job_ptrs:
-            self._build_jobs()
-            self._job_ptrs = ptrs
         # the first two layers' weights on this stream; the other 21 layers (99.9 % of the bytes) on the side
         # stream, overlapping im2col + enc1 (forward() joins before enc2)
         tab, n, tiles = self.pack_jobs[0]
@@ -172,9 +190,10 @@ class UNetEngine:
                               0, 0, 0])
             t0[grp] += n
 
-        def add_unpack(g, D, grad, A, B, T, ldA, ldB, transposed=0):
+        def add_unpack(g, D, grad, A, B, T, ldA, ldB, transposed=0, nsplit=1, sstride=0):
             n, tb = self._tiles(A, B)
-            unpack[g].append([D.data_ptr(), grad.data_ptr(), A, B, T, ldA, ldB, one, 0, ut0[g], tb, transposed, 0, 0, 0, 0])
+            unpack[g].append([D.data_ptr(), grad.data_ptr(), A, B, T, ldA, ldB, one, 0, ut0[g], tb, transposed, nsplit,
+                              sstride, 0, 0])
             ut0[g] += n
 
         def add_cvt(g, src, dst, n):
@@ -190,7 +209,8 @@ class UNetEngine:
             else:
                 ci = u.c0 + u.c1
                 add_pack(w, u.wf, u.wd, u.cout, ci, 9, u.cout, ci, ci, u.cout, 1, grp=0 if i < 2 else 1)
-                add_unpack(g, u.gp, self.gview[w], u.cout, ci, 9, u.cout, ci, transposed=1)
+                add_unpack(g, u.part, self.gview[w], u.cout, ci, 9, u.cout, ci, transposed=1, nsplit=u.nsplit,
+                           sstride=9 * ci * u.cout)
             add_cvt(g, u.dbias, self.gview[u.conv.bias], u.cout)
         for j, (mod, cm, co) in enumerate(self.convT):
             add_pack(mod.weight, self.twd[j], self.twf[j], cm, co, 4, cm, co, co, cm, 0)
@@ -252,6 +272,7 @@ class UNetEngine:
         if cin != self.m.in_dim:
             raise ValueError(f"expected {self.m.in_dim} input channels, got {cin}")
         self._setup(x.device)
+        self._ensure_wgrad_bufs(n, h, w)
         self._pack_weights()
         self.training_fwd = training
         if training:
@@ -307,7 +328,7 @@ class UNetEngine:
             if u.stem:
                 ops.gemm_wgrad(dpre, u.x0, out=u.gp)
             else:
-                ops.conv3x3_wgrad(dpre, u.x0, u.x1, out=u.gp)
+                ops.conv3x3_wgrad_split(dpre, u.x0, u.x1, out=u.part)
         if u.stem or not need_dx:
             return None, None
         return ops.conv3x3_dgrad(dpre, u.wd, u.c0, u.c1)

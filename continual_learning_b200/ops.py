@@ -126,6 +126,27 @@ def conv3x3_wgrad(dy, x0, x1=None, out=None):
     return dw
 
 
+def conv3x3_wgrad_splits(cout, cin, n, h, w):
+    """number of split-K partial buffers clk_conv3x3_wgrad_split writes for this shape (host-side query)."""
+    k = _lib.load().clk_conv3x3_wgrad_splits(cout, cin, n, h, w)
+    if k < 0:
+        _lib.check(k)
+    return k
+
+
+def conv3x3_wgrad_split(dy, x0, x1=None, out=None):
+    """deterministic split-K weight gradient: returns fp32 [nsplit, 9, Cin, Cout] partial sums (plain stores)."""
+    _dev(dy)
+    n, h, w, cout = dy.shape
+    c0 = x0.shape[3]
+    c1 = 0 if x1 is None else x1.shape[3]
+    if out is None:
+        out = torch.empty((conv3x3_wgrad_splits(cout, c0 + c1, n, h, w), 9, c0 + c1, cout), device=dy.device,
+                          dtype=torch.float32)
+    _lib.call("clk_conv3x3_wgrad_split", dy, cout, x0, c0, x1, c1, out, n, h, w)
+    return out
+
+
 def gemm_fprop(a, w, bias, n_store, out_f32=False, relu=False, stats=None, out=None):
     """a bf16 [..., K] (rows = pixels), w bf16 [Npad, K]; returns [..., n_store or Npad]."""
     _dev(a)

@@ -61,7 +61,7 @@ int clk_unpack_wgrad(const float* D, float* grad, int A, int B, int T, int ldA, 
 /* Batched (table-driven) forms: ONE launch for every layer of the model. `jobs` is a device array of
  * int64[16] rows (pointers and ints widened to int64, alpha as the bit pattern of a double):
  *   pack:    {src, outAB, outBA, A, B, T, ldA, ldB, ldB2, ldA2, rev, tile0, tiles_b}
- *   unpack:  {D, grad, A, B, T, ldA, ldB, alpha, accumulate, tile0, tiles_b, transposed}
+ *   unpack:  {D, grad, A, B, T, ldA, ldB, alpha, accumulate, tile0, tiles_b, transposed, nsplit, split_stride}
  *   convert: {src_f64, dst_f32, n, ld_group, groups, alpha, accumulate}   (one block per row)
  * tile0 = index of the job's first 32x32 tile in the launch grid, tiles_b = ceil(B/32). */
 int clk_pack_w_multi(const void* jobs, int njobs, int total_tiles, int max_T, clk_stream_t st);
@@ -85,6 +85,12 @@ int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C
  * Caller zeroes dw; clk_unpack_wgrad(..., transposed=1) turns it into the PyTorch [Cout][Cin][3][3] layout. */
 int clk_conv3x3_wgrad(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* dw,
                       int N, int H, int W, clk_stream_t st);
+/* Deterministic split-K form used by the step: K split s stores its partial sums to partials + s*9*Cin*Cout with
+ * plain stores (no atomics, nothing to zero); clk_conv3x3_wgrad_splits() returns the number of splits the kernel
+ * will use for a shape (pure host function), and clk_unpack_wgrad_multi sums the partials in a fixed order. */
+int clk_conv3x3_wgrad_splits(int Cout, int Cin, int N, int H, int W);
+int clk_conv3x3_wgrad_split(const void* dy, int Cout, const void* x0, int C0, const void* x1, int C1, float* partials,
+                            int N, int H, int W, clk_stream_t st);
 /* plain GEMM out[P][.] = a[P][K] * w[Npad][K]^T (+bias, ReLU, stats): the im2col'ed stem conv
  * (models/unet.py:50), the 1x1 head (models/unet.py:72; fp32 output, n_store = num_classes) and the
  * head dgrad.  K % 64 == 0; Npad in {32 (f32 out), 64, 128, 256 multiples}. */
