@@ -35,6 +35,7 @@ SIGNATURES = {
     "clk_pack_w_multi": [p, i, i, i, p],
     "clk_unpack_wgrad_multi": [p, i, i, i, p],
     "clk_f64_to_f32_multi": [p, i, p],
+    "clk_reduce_partials_multi": [p, i, i, p],
     "clk_conv3x3_fprop": [p, i, p, i, p, p, p, p, p, i, i, i, i, i, p],
     "clk_conv3x3_dgrad": [p, i, p, p, i, p, i, i, i, i, p],
     "clk_conv3x3_wgrad": [p, i, p, i, p, i, p, i, i, i, p],

@@ -268,6 +268,10 @@ int clk_unpack_wgrad_multi(const void* jobs, int njobs, int total_tiles, int max
   if (!jobs || njobs <= 0 || total_tiles < 0 || max_T <= 0 || max_T > 9) return fail(CLK_E_BADARG, "unpack_wgrad_multi: bad args");
   return cuda_status(unpack_wgrad_multi(jobs, njobs, total_tiles, max_T, S(st)), "unpack_wgrad_multi");
 }
+int clk_reduce_partials_multi(const void* jobs, int njobs, int total_blocks, clk_stream_t st) {
+  if (!jobs || njobs <= 0 || total_blocks < 0) return fail(CLK_E_BADARG, "reduce_partials_multi: bad args");
+  return cuda_status(reduce_partials_multi(jobs, njobs, total_blocks, S(st)), "reduce_partials_multi");
+}
 int clk_f64_to_f32_multi(const void* jobs, int njobs, clk_stream_t st) {
   if (!jobs || njobs <= 0) return fail(CLK_E_BADARG, "f64_to_f32_multi: bad args");
   return cuda_status(f64_to_f32_multi(jobs, njobs, S(st)), "f64_to_f32_multi");

@@ -1395,6 +1395,40 @@ cudaError_t unpack_wgrad_multi(const void* jobs, int njobs, int total_tiles, int
   return cudaGetLastError();
 }
 
+// split-K partial buffers -> their sum, in place in split 0 (fixed summation order: deterministic).
+// row: {base, n_vec4, nsplit, stride_vec4, block0}; one thread per float4, 8 independent loads in flight.
+__global__ void __launch_bounds__(256) reduce_partials_multi_kernel(const long long* __restrict__ jobs, int njobs) {
+  const int j = find_job(jobs, njobs, blockIdx.x, 4);
+  const long long* J = jobs + j * 16;
+  float4* base = reinterpret_cast<float4*>(J[0]);
+  const long long nvec = J[1];
+  const int nsplit = static_cast<int>(J[2]);
+  const long long stride = J[3];
+  const long long i = (static_cast<long long>(blockIdx.x) - J[4]) * blockDim.x + threadIdx.x;
+  if (i >= nvec || nsplit <= 1) return;
+  float4 acc = base[i];
+  int sp = 1;
+  for (; sp + 8 <= nsplit; sp += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = base[i + (sp + u) * stride];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+    }
+  }
+  for (; sp < nsplit; ++sp) {
+    const float4 v = base[i + sp * stride];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  base[i] = acc;
+}
+cudaError_t reduce_partials_multi(const void* jobs, int njobs, int total_blocks, cudaStream_t st) {
+  if (total_blocks <= 0) return cudaSuccess;
+  reduce_partials_multi_kernel<<<total_blocks, 256, 0, st>>>(static_cast<const long long*>(jobs), njobs);
+  return cudaGetLastError();
+}
+
 // row: {src f64, dst f32, n, ld_group, groups, alpha (double bits), accumulate}; one block per job
 __global__ void f64_to_f32_multi_kernel(const long long* __restrict__ jobs) {
   const long long* J = jobs + blockIdx.x * 16;

@@ -70,6 +70,7 @@ cudaError_t bn_relu_bwd_apply_fused(const void* dz, const void* y, void* dpre, c
                                     cudaStream_t st);
 cudaError_t pack_w_multi(const void* jobs, int njobs, int total_tiles, int max_T, cudaStream_t st);
 cudaError_t unpack_wgrad_multi(const void* jobs, int njobs, int total_tiles, int max_T, cudaStream_t st);
+cudaError_t reduce_partials_multi(const void* jobs, int njobs, int total_blocks, cudaStream_t st);
 cudaError_t f64_to_f32_multi(const void* jobs, int njobs, cudaStream_t st);
 
 }  // namespace clk

@@ -180,6 +180,7 @@ class UNetEngine:
         nc = self.m.num_classes
         pack, t0 = [[], []], [0, 0]
         unpack = [[], []]   # group 0: head + decoder (final first in backward), group 1: encoder
+        reduce_, rb0 = [[], []], [0, 0]
         cvt = [[], []]
         ut0 = [0, 0]
 
@@ -209,8 +210,11 @@ class UNetEngine:
             else:
                 ci = u.c0 + u.c1
                 add_pack(w, u.wf, u.wd, u.cout, ci, 9, u.cout, ci, ci, u.cout, 1, grp=0 if i < 2 else 1)
-                add_unpack(g, u.part, self.gview[w], u.cout, ci, 9, u.cout, ci, transposed=1, nsplit=u.nsplit,
-                           sstride=9 * ci * u.cout)
+                add_unpack(g, u.part, self.gview[w], u.cout, ci, 9, u.cout, ci, transposed=1)
+                if u.nsplit > 1:  # sum the split-K partials into split 0 first (one batched launch per group)
+                    nvec = 9 * ci * u.cout // 4
+                    reduce_[g].append([u.part.data_ptr(), nvec, u.nsplit, nvec, rb0[g]] + [0] * 11)
+                    rb0[g] += (nvec + 255) // 256
             add_cvt(g, u.dbias, self.gview[u.conv.bias], u.cout)
         for j, (mod, cm, co) in enumerate(self.convT):
             add_pack(mod.weight, self.twd[j], self.twf[j], cm, co, 4, cm, co, co, cm, 0)
@@ -226,9 +230,13 @@ class UNetEngine:
         self.pack_jobs = [(dev_table(pack[g]), len(pack[g]), t0[g]) for g in range(2)]
         self.unpack_jobs = [(dev_table(unpack[g]), len(unpack[g]), ut0[g]) for g in range(2)]
         self.cvt_jobs = [(dev_table(cvt[g]), len(cvt[g])) for g in range(2)]
+        self.reduce_jobs = [((dev_table(reduce_[g]) if reduce_[g] else None), len(reduce_[g]), rb0[g]) for g in range(2)]
 
     def _flush_grads(self, g):
         self._join()  # weight gradients run on the side stream
+        tab, n, blocks = self.reduce_jobs[g]
+        if n:
+            _lib.call("clk_reduce_partials_multi", tab, n, blocks)
         tab, n, tiles = self.unpack_jobs[g]
         _lib.call("clk_unpack_wgrad_multi", tab, n, tiles, 9)
         tab, n = self.cvt_jobs[g]

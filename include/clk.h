@@ -67,6 +67,9 @@ int clk_unpack_wgrad(const float* D, float* grad, int A, int B, int T, int ldA, 
 int clk_pack_w_multi(const void* jobs, int njobs, int total_tiles, int max_T, clk_stream_t st);
 int clk_unpack_wgrad_multi(const void* jobs, int njobs, int total_tiles, int max_T, clk_stream_t st);
 int clk_f64_to_f32_multi(const void* jobs, int njobs, clk_stream_t st);
+/* split-K partial buffers -> their sum, in place in split 0, fixed order (deterministic).
+ *   reduce:  {base, n_float4, nsplit, stride_float4, block0}  (256 float4 per block; block0 = first block of the job) */
+int clk_reduce_partials_multi(const void* jobs, int njobs, int total_blocks, clk_stream_t st);
 
 /* ---- tcgen05 implicit GEMMs ----
  * conv3x3, stride 1, zero pad 1 (nn.Conv2d at models/unet.py:13,16,28,31,53,66,69) fused with

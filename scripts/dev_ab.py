@@ -39,7 +39,7 @@ if __name__ == "__main__":
     variants = [("default", {}, {}), ("fuse_bn", dict(fuse_bn=True), {}), ("no side_pack", dict(side_pack=False), {}),
                 ("no side stream", dict(use_side_stream=False, side_pack=False), {}),
                 ("default (repeat)", {}, {}), ("fprop_bn=64", {}, {"fprop_bn": 64}), ("conv3 generic only", {}, {"conv3_v2": 0}),
-                ("conv3 halo 1-CTA everywhere", {}, {"conv3_v2": 2, "conv3_pair": 0}), ("conv3 hybrid (round-1 mid)", {}, {"conv3_v2": 1, "conv3_pair": 1}), ("wgrad generic", {}, {"wgrad_v2": 0}), ("default (again)", {}, {"fprop_bn": 0, "conv3_v2": 4, "wgrad_v2": 1})]
+                ("conv3 halo 1-CTA everywhere", {}, {"conv3_v2": 2, "conv3_pair": 0}), ("conv3 hybrid (round-1 mid)", {}, {"conv3_v2": 1, "conv3_pair": 1}), ("default (again)", {}, {"fprop_bn": 0, "conv3_v2": 4, "wgrad_v2": 1})]
     for extra in sys.argv[1:]:
         k, v = extra.split("=")
         variants.append((extra, {}, {k: int(v)}))
