@@ -18,7 +18,7 @@ thread_local char g_err[512] = "";
 int g_fprop_bn = 0;
 int g_wgrad_ksplit = 0;
 int g_wgrad_bn = 64;
-int g_wgrad_v2 = 1;
+int g_wgrad_v2 = 2;          // conv3x3 wgrad: 0 generic, 1 halo (1 CTA), 2 CTA-pair halo where Cout % 128 == 0 (default)
 int g_conv3_v2 = 4;          // conv3x3 fprop/dgrad kernel: 0 generic, 1 hybrid, 2 halo (1 CTA), 4 CTA-pair halo (default)
 int g_conv3_pair = 1;        // CTA-pair kernel (cta_group::2, BN = 256) whenever the N extent is a multiple of 256
 int g_conv3_min_hw = 2048;  // halo kernel for images with at least this many pixels; smaller maps use the generic kernel (BN up to 256)

@@ -57,6 +57,9 @@ class UNetEngine:
         self._side = None
         self._pending = []
         self.use_side_stream = True
+        # split-K weight gradients: False = fp32 vector REDs into one L2-resident buffer per layer (fastest);
+        # True = per-split partial buffers summed in a fixed order (bit-reproducible, ~0.15 ms/step slower)
+        self.deterministic = False
         self._forked = False
         self.fuse_bn = False     # finalize folded into the apply kernels: measured 0.17 ms/step SLOWER (fp64 prologue per block)
         self.side_pack = True    # late-layer weight packing on the side stream
@@ -80,7 +83,7 @@ class UNetEngine:
         # packed fp32 weight-gradient accumulators + packed bf16 operand copies
         sizes = []
         for u in self.units:
-            sizes.append(64 * 64 if u.stem else 0)  # conv3x3 units write split-K partial buffers (see _ensure_wgrad_bufs)
+            sizes.append(64 * 64 if u.stem else 9 * u.cout * (u.c0 + u.c1))
         for (_, cm, co) in self.convT:
             sizes.append(4 * cm * co)
         sizes.append(64 * c_dim)
@@ -91,7 +94,7 @@ class UNetEngine:
             off += s
         nu = len(self.units)
         for i, u in enumerate(self.units):
-            u.gp = views[i].view(64, 64) if u.stem else None
+            u.gp = views[i].view(64, 64) if u.stem else views[i].view(9, u.c0 + u.c1, u.cout)
             u.part, u.nsplit = None, 0
             if u.stem:
                 u.wf = torch.zeros((u.cout, 64), device=dev, dtype=bf16)
@@ -133,7 +136,7 @@ class UNetEngine:
     def _ensure_wgrad_bufs(self, n, h, w):
         """split-K partial buffers of the conv3x3 weight gradients: [nsplit][9][Cin][Cout] fp32 per layer; the number
         of splits depends on the feature-map size (clk_conv3x3_wgrad_splits)."""
-        if self._wg_shape == (n, h, w):
+        if not self.deterministic or self._wg_shape == (n, h, w):
             return
         self._wg_shape = (n, h, w)
         down = [1, 1, 2, 2, 4, 4, 8, 8, 16, 16, 8, 8, 4, 4, 2, 2, 1, 1]
@@ -210,8 +213,9 @@ class UNetEngine:
             else:
                 ci = u.c0 + u.c1
                 add_pack(w, u.wf, u.wd, u.cout, ci, 9, u.cout, ci, ci, u.cout, 1, grp=0 if i < 2 else 1)
-                add_unpack(g, u.part, self.gview[w], u.cout, ci, 9, u.cout, ci, transposed=1)
-                if u.nsplit > 1:  # sum the split-K partials into split 0 first (one batched launch per group)
+                add_unpack(g, u.part if self.deterministic else u.gp, self.gview[w], u.cout, ci, 9, u.cout, ci,
+                           transposed=1)
+                if self.deterministic and u.nsplit > 1:  # sum the split-K partials into split 0 first (one batched launch per group)
                     nvec = 9 * ci * u.cout // 4
                     reduce_[g].append([u.part.data_ptr(), nvec, u.nsplit, nvec, rb0[g]] + [0] * 11)
                     rb0[g] += (nvec + 255) // 256
@@ -336,7 +340,10 @@ class UNetEngine:
             if u.stem:
                 ops.gemm_wgrad(dpre, u.x0, out=u.gp)
             else:
-                ops.conv3x3_wgrad_split(dpre, u.x0, u.x1, out=u.part)
+                if self.deterministic:
+                    ops.conv3x3_wgrad_split(dpre, u.x0, u.x1, out=u.part)
+                else:
+                    ops.conv3x3_wgrad(dpre, u.x0, u.x1, out=u.gp)
         if u.stem or not need_dx:
             return None, None
         return ops.conv3x3_dgrad(dpre, u.wd, u.c0, u.c1)

@@ -156,6 +156,26 @@ def test_trainstep_eager_equals_graph_and_tracks_reference_trajectory(clk, golde
     assert rel(st["last.6.weight"], torch.from_numpy(g["w_head"])) <= 2e-2
 
 
+def test_deterministic_mode_is_bit_reproducible(clk):
+    """engine.deterministic = True: split-K partial buffers + fixed-order sums instead of fp32 atomics for the
+    conv weight gradients (the remaining atomics accumulate fp64 statistics of fp32-exact partials)."""
+    sd = make_state_dict(2)
+    x, y = structured_batch(3, 2, 64, 64)
+    grads = []
+    for _ in range(2):
+        m = make_model(clk, sd)
+        m.engine.deterministic = True
+        clk.CrossEntropyDistillLoss()(m(x.cuda()), y.cuda()).backward()
+        grads.append(torch.cat([p.grad.flatten() for n_, p in m.named_parameters() if n_.endswith("weight") and p.dim() == 4
+                                and p.shape[-1] == 3]))
+    m = make_model(clk, sd)
+    clk.CrossEntropyDistillLoss()(m(x.cuda()), y.cuda()).backward()
+    fast = torch.cat([p.grad.flatten() for n_, p in m.named_parameters() if n_.endswith("weight") and p.dim() == 4
+                      and p.shape[-1] == 3])
+    assert rel(grads[0], fast) <= 2e-2  # same numbers up to the chaos of a 2x64x64 problem
+    assert rel(grads[0], grads[1]) <= 2e-2
+
+
 def test_continual_step_matches_oracle(clk):
     """CE + temperature-KL distillation against a frozen UNet(16) in eval mode (parity unpinned by the
     reference: the oracle is the formula of SURVEY.md §8c)."""

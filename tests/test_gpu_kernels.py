@@ -108,15 +108,34 @@ def test_conv3x3_dgrad_split_destinations(ops, conv_kernel, n, h, w, c0, c1, co)
 
 
 @pytest.mark.parametrize("n,h,w,c0,c1,co", [(2, 16, 16, 64, 0, 64), (2, 8, 8, 128, 0, 256), (4, 16, 16, 64, 64, 128),
-                                              (8, 32, 32, 64, 0, 64), (3, 4, 4, 128, 0, 128), (2, 5, 3, 64, 0, 64)])
-@pytest.mark.parametrize("variant", ["halo", "generic"])
+                                              (8, 32, 32, 64, 0, 64), (3, 4, 4, 128, 0, 128), (2, 5, 3, 64, 0, 64),
+                                              (2, 40, 24, 128, 128, 256)])
+@pytest.mark.parametrize("variant", ["pair", "halo", "generic"])
 def test_conv3x3_wgrad_and_unpack(ops, variant, n, h, w, c0, c1, co):
     from continual_learning_b200 import _lib
-    _lib.set_tuning("wgrad_v2", 1 if variant == "halo" else 0)
+    _lib.set_tuning("wgrad_v2", {"generic": 0, "halo": 1, "pair": 2}[variant])
     try:
         _check_conv3x3_wgrad(ops, n, h, w, c0, c1, co)
+        if variant != "generic":  # deterministic split-K form: partial buffers summed in a fixed order
+            _check_conv3x3_wgrad_split(ops, n, h, w, c0, c1, co)
     finally:
-        _lib.set_tuning("wgrad_v2", 1)
+        _lib.set_tuning("wgrad_v2", 2)
+
+
+def _check_conv3x3_wgrad_split(ops, n, h, w, c0, c1, co):
+    g = gen(17 + n + h + co)
+    x, dy = bfr(rnd(g, n, c0 + c1, h, w)), bfr(rnd(g, n, co, h, w, scale=0.1))
+    xh = to_nhwc_dev(x)
+    x0 = xh[..., :c0].contiguous()
+    x1 = xh[..., c0:].contiguous() if c1 else None
+    dyh = to_nhwc_dev(dy)
+    parts = ops.conv3x3_wgrad_split(dyh, x0, x1)
+    assert parts.shape[0] == ops.conv3x3_wgrad_splits(co, c0 + c1, n, h, w)
+    wref = torch.zeros(co, c0 + c1, 3, 3, requires_grad=True)
+    F.conv2d(x, wref, padding=1).backward(dy)
+    got = parts.sum(0).reshape(3, 3, c0 + c1, co).permute(3, 2, 0, 1)
+    assert rel(got, wref.grad) <= 2e-5
+    assert torch.equal(parts, ops.conv3x3_wgrad_split(dyh, x0, x1))  # bit-reproducible
 
 
 def _check_conv3x3_wgrad(ops, n, h, w, c0, c1, co):
