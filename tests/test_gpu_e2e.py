@@ -160,7 +160,7 @@ def test_deterministic_mode_is_bit_reproducible(clk):
     """engine.deterministic = True: split-K partial buffers + fixed-order sums instead of fp32 atomics for the
     conv weight gradients (the remaining atomics accumulate fp64 statistics of fp32-exact partials)."""
     sd = make_state_dict(2)
-    x, y = structured_batch(3, 2, 64, 64)
+    x, y = structured_batch(3, 4, 128, 128)
     grads = []
     for _ in range(2):
         m = make_model(clk, sd)
@@ -172,7 +172,8 @@ def test_deterministic_mode_is_bit_reproducible(clk):
     clk.CrossEntropyDistillLoss()(m(x.cuda()), y.cuda()).backward()
     fast = torch.cat([p.grad.flatten() for n_, p in m.named_parameters() if n_.endswith("weight") and p.dim() == 4
                       and p.shape[-1] == 3])
-    assert rel(grads[0], fast) <= 2e-2  # same numbers up to the chaos of a 2x64x64 problem
+    # same numbers as the RED path and as a second run, up to the fp32 summation order of the BatchNorm statistics
+    assert rel(grads[0], fast) <= 2e-2
     assert rel(grads[0], grads[1]) <= 2e-2
 
 
