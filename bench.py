@@ -28,6 +28,9 @@ UNIT = "images/s"
 BATCH, H, W, NUM_CLASSES = 16, 256, 256, 21
 GFLOP_PER_IMG_TRAIN = 289.28  # 3x fwd - dgrad(enc1.0), true (unpadded) dims, 256x256
 WORKLOAD = "unet21_256x256_b16_train_single_task"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, mean over the 34 launches of one
+# step (bytes), from the `ncu --set full` capture summarised in profiles/round1_pair_kernels_ncu_full.md
+ROOFLINE_TRAFFIC = 87.1e6
 
 
 def igemm_flops_per_step(batch, h, w, conv_dim=64, num_classes=NUM_CLASSES, in_dim=3):
@@ -42,14 +45,17 @@ def igemm_flops_per_step(batch, h, w, conv_dim=64, num_classes=NUM_CLASSES, in_d
         convT.append((cm, co, d))
     convs += [(2 * c, c, 1, True), (c, c, 1, True)]
     total = 0.0
+    conv_fd = 0.0  # conv3x3 forward + dgrad launches only (the dominant kernel, igemm_conv3x2_kernel)
     for ci, co, d, has_dgrad in convs:
         m = batch * (h // d) * (w // d)
         total += 2.0 * m * co * ci * 9 * (3 if has_dgrad else 2)
+        if ci != in_dim:  # the 3-channel stem runs as an im2col GEMM on the generic kernel
+            conv_fd += 2.0 * m * co * ci * 9 * 2
     for cm, co, d in convT:
         m = batch * (h // d) * (w // d)
         total += 2.0 * m * (4 * co) * cm * 3
     total += 2.0 * batch * h * w * num_classes * c * 3
-    return total
+    return total, conv_fd
 
 
 class ClockSampler:
@@ -244,18 +250,28 @@ def run_b200(args):
     model.engine.use_side_stream = False  # serialise the weight-gradient stream: one kernel at a time under the events
     ts_prof.step(*devb[0])
     torch.cuda.synchronize()
-    _lib.start_profile()
-    ts_prof.step(*devb[1])
-    prof = _lib.stop_profile()
+    PROF_STEPS = 3
+    prof = {}
+    for i in range(PROF_STEPS):
+        _lib.start_profile()
+        ts_prof.step(*devb[(i + 1) % len(devb)])
+        for k, v in _lib.stop_profile().items():
+            e = prof.setdefault(k, [0, 0.0])
+            e[0] += v[0] / PROF_STEPS
+            e[1] += v[1] / PROF_STEPS
     model.engine.use_side_stream = True
     igemm_names = [k for k in prof if k.startswith(("clk_conv3x3_", "clk_gemm_", "clk_convT2x2_"))]
     igemm_ms = sum(prof[k][1] for k in igemm_names)
     igemm_n = sum(prof[k][0] for k in igemm_names)
     all_ms = sum(v[1] for v in prof.values())
-    flops = igemm_flops_per_step(BATCH, H, W)
+    flops, conv_fd_flops = igemm_flops_per_step(BATCH, H, W)
     peak_tf, peak_hbm, peak_src = measured_peaks()
-    achieved_tf = flops / (igemm_ms / 1e3) / 1e12
-    breakdown = {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    all_tensor_tf = flops / (igemm_ms / 1e3) / 1e12
+    # dominant kernel: igemm_conv3x2_kernel = the 17 conv3x3 forward + 17 dgrad launches of a step
+    dom_n = prof["clk_conv3x3_fprop"][0] + prof["clk_conv3x3_dgrad"][0]
+    dom_ms = prof["clk_conv3x3_fprop"][1] + prof["clk_conv3x3_dgrad"][1]
+    achieved_tf = conv_fd_flops / (dom_ms / 1e3) / 1e12
+    breakdown = {k: {"launches": round(v[0]), "ms": round(v[1], 4)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
 
     if world > 1:
         dist.barrier()
@@ -282,12 +298,20 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "wall_ms_per_step": wall_e2e * 1e3 / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "igemm_fprop_kernel/igemm_wgrad_kernel (all tcgen05 conv/convT/1x1 launches of a step)",
+        "roofline": {"bound": "tensor",
+                     "kernel": "igemm_conv3x2_kernel (conv3x3 forward + dgrad, CTA-pair tcgen05 halo kernel)",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "peak_source": peak_src, "traffic": None, "launches_per_step": igemm_n,
-                     "igemm_ms_per_step": igemm_ms, "all_kernels_ms_per_step": all_ms,
-                     "igemm_share_of_step": igemm_ms / all_ms if all_ms else None,
-                     "algorithmic_gflop_per_step": flops / 1e9},
+                     "peak_source": peak_src, "traffic": ROOFLINE_TRAFFIC,
+                     "launches_per_step": round(dom_n), "avg_launch_us": dom_ms * 1e3 / dom_n,
+                     "algorithmic_gflop_per_launch": conv_fd_flops / dom_n / 1e9,
+                     "share_of_step": dom_ms / all_ms if all_ms else None,
+                     "timing": f"CUDA events around every launch of {PROF_STEPS} eager steps run right after the "
+                               "timed region (same process, same buffers, weight-gradient side stream serialised)",
+                     "all_tensor_kernels": {"achieved": all_tensor_tf, "frac": all_tensor_tf / peak_tf,
+                                            "launches_per_step": round(igemm_n), "ms_per_step": igemm_ms,
+                                            "share_of_step": igemm_ms / all_ms if all_ms else None,
+                                            "algorithmic_gflop_per_step": flops / 1e9},
+                     "all_kernels_ms_per_step": all_ms},
         "kernel_breakdown_ms": breakdown,
         "loss_last_step": last_loss,
         "cpu_baseline": cpu,
