@@ -37,10 +37,12 @@ SIGNATURES = {
     "clk_f64_to_f32_multi": [p, i, p],
     "clk_reduce_partials_multi": [p, i, i, p],
     "clk_conv3x3_fprop": [p, i, p, i, p, p, p, p, p, i, i, i, i, i, p],
+    "clk_conv3x3_fprop_eval": [p, i, p, i, p, p, p, p, p, i, i, i, i, i, p],
     "clk_conv3x3_dgrad": [p, i, p, p, i, p, i, i, i, i, p],
     "clk_conv3x3_wgrad": [p, i, p, i, p, i, p, i, i, i, p],
     "clk_conv3x3_wgrad_split": [p, i, p, i, p, i, p, i, i, i, p],
     "clk_gemm_fprop": [p, i, p, p, p, i, i, i, i, p, p, ll, i, p],
+    "clk_gemm_fprop_eval": [p, i, p, p, p, i, i, i, p, p, ll, i, p],
     "clk_gemm_wgrad": [p, i, p, i, p, i, i, ll, p],
     "clk_convT2x2_fprop": [p, p, p, p, i, i, i, i, i, p],
     "clk_convT2x2_dgrad": [p, p, p, i, i, i, i, i, p],

@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [nvcc, "-shared", "-o", LIB, *objs]  # cudart is linked statically (nvcc default)
+    cmd = [nvcc, "-shared", "-Wno-deprecated-gpu-targets", "-o", LIB, *objs]  # cudart is linked statically (nvcc default)
     subprocess.run(cmd, check=True)
     return LIB
 

@@ -278,10 +278,12 @@ int clk_f64_to_f32_multi(const void* jobs, int njobs, clk_stream_t st) {
 }
 
 // ------------------------------------------------------------------ igemm: conv3x3
-int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias,
-                      void* y, double* stat_sum, double* stat_sq, int N, int H, int W, int Cout, int relu,
-                      clk_stream_t st) {
+static int conv3x3_fprop_impl(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias,
+                             void* y, double* stat_sum, double* stat_sq, const float* bn_scale,
+                             const float* bn_shift, int N, int H, int W, int Cout, int relu, clk_stream_t st) {
   if (!x0 || !w || !y || N <= 0 || H <= 0 || W <= 0) return fail(CLK_E_BADARG, "conv3x3_fprop: bad args");
+  if ((bn_scale == nullptr) != (bn_shift == nullptr) || (bn_scale && stat_sum))
+    return fail(CLK_E_BADARG, "conv3x3_fprop: scale and shift come together and exclude the statistics");
   if (C0 % 64 || C1 % 64 || Cout % 64 || C0 <= 0 || (x1 == nullptr) != (C1 == 0))
     return fail(CLK_E_UNSUPPORTED_SHAPE, "conv3x3_fprop: channels must be multiples of 64 (C0=%d C1=%d Cout=%d)",
                 C0, C1, Cout);
@@ -306,6 +308,8 @@ int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void
     q.relu = relu;
     q.stat_sum = stat_sum;
     q.stat_sq = stat_sq;
+    q.bn_scale = bn_scale;
+    q.bn_shift = bn_shift;
     CUtensorMap a0, a1, b;
     const int bw = (pair && BNq == 256) ? 16 : 24;
     if (pair && BNq != 256) {  // two sub tiles per CTA: the pair covers 16 x 32 pixels
@@ -333,6 +337,8 @@ int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void
   p.relu = relu;
   p.stat_sum = stat_sum;
   p.stat_sq = stat_sq;
+  p.bn_scale = bn_scale;
+  p.bn_shift = bn_shift;
   const int BN = pick_bn(Cout);
   CUtensorMap a0, a1, b;
   CHECK_RC(map_nhwc(&a0, x0, N, H, W, C0, p.g.tw, p.g.th, p.g.nb));
@@ -340,6 +346,19 @@ int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void
   else a1 = a0;
   CHECK_RC(map_weights(&b, w, 9, Cout, C0 + C1, BN));
   return cuda_status(launch_fprop(BN, 0, a0, a1, b, p, num_tiles(p.g), Cout / BN, S(st)), "conv3x3_fprop");
+}
+
+int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias,
+                      void* y, double* stat_sum, double* stat_sq, int N, int H, int W, int Cout, int relu,
+                      clk_stream_t st) {
+  return conv3x3_fprop_impl(x0, C0, x1, C1, w, bias, y, stat_sum, stat_sq, nullptr, nullptr, N, H, W, Cout, relu, st);
+}
+
+int clk_conv3x3_fprop_eval(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias,
+                           void* z, const float* bn_scale, const float* bn_shift, int N, int H, int W, int Cout,
+                           int relu, clk_stream_t st) {
+  if (!bn_scale || !bn_shift) return fail(CLK_E_BADARG, "conv3x3_fprop_eval: scale / shift missing");
+  return conv3x3_fprop_impl(x0, C0, x1, C1, w, bias, z, nullptr, nullptr, bn_scale, bn_shift, N, H, W, Cout, relu, st);
 }
 
 int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C0, void* dx1, int C1, int N,
@@ -504,10 +523,12 @@ int clk_conv3x3_wgrad(const void* dy, int Cout, const void* x0, int C0, const vo
 }
 
 // ------------------------------------------------------------------ igemm: plain GEMMs
-int clk_gemm_fprop(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
-                   int out_is_f32, int relu, double* stat_sum, double* stat_sq, long long P, int Npad,
-                   clk_stream_t st) {
+static int gemm_fprop_impl(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
+                          int out_is_f32, int relu, double* stat_sum, double* stat_sq, const float* bn_scale,
+                          const float* bn_shift, long long P, int Npad, clk_stream_t st) {
   if (!a || !w || !out || P <= 0) return fail(CLK_E_BADARG, "gemm_fprop: bad args");
+  if ((bn_scale == nullptr) != (bn_shift == nullptr) || (bn_scale && stat_sum))
+    return fail(CLK_E_BADARG, "gemm_fprop: scale and shift come together and exclude the statistics");
   if (K % 64 || K <= 0) return fail(CLK_E_UNSUPPORTED_SHAPE, "gemm_fprop: K must be a multiple of 64 (K=%d)", K);
   if (P > 2000000000LL) return fail(CLK_E_UNSUPPORTED_SHAPE, "gemm_fprop: P too large");
   int BN;
@@ -530,10 +551,26 @@ int clk_gemm_fprop(const void* a, int K, const void* w, const float* bias, void*
   p.relu = relu;
   p.stat_sum = stat_sum;
   p.stat_sq = stat_sq;
+  p.bn_scale = bn_scale;
+  p.bn_shift = bn_shift;
   CUtensorMap a0, b;
   CHECK_RC(map_linear(&a0, a, P, K, 128));
   CHECK_RC(map_weights(&b, w, 1, Npad, K, BN));
   return cuda_status(launch_fprop(BN, out_is_f32, a0, a0, b, p, num_tiles(p.g), Npad / BN, S(st)), "gemm_fprop");
+}
+
+int clk_gemm_fprop(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
+                   int out_is_f32, int relu, double* stat_sum, double* stat_sq, long long P, int Npad,
+                   clk_stream_t st) {
+  return gemm_fprop_impl(a, K, w, bias, out, ldo, n_store, out_is_f32, relu, stat_sum, stat_sq, nullptr, nullptr, P,
+                         Npad, st);
+}
+
+int clk_gemm_fprop_eval(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
+                        int relu, const float* bn_scale, const float* bn_shift, long long P, int Npad,
+                        clk_stream_t st) {
+  if (!bn_scale || !bn_shift) return fail(CLK_E_BADARG, "gemm_fprop_eval: scale / shift missing");
+  return gemm_fprop_impl(a, K, w, bias, out, ldo, n_store, 0, relu, nullptr, nullptr, bn_scale, bn_shift, P, Npad, st);
 }
 
 int clk_gemm_wgrad(const void* u, int CU, const void* t, int CT, float* out, int ld_u, int ld_t, long long P,

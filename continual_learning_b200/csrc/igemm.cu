@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
     const int m = q * 32 + lane;
     const int etid = threadIdx.x - 64;
     const bool do_stats = p.stat_sum != nullptr;
+    const bool affine = p.bn_scale != nullptr;
     float* scratch = scratch_all + (warp - 2) * (32 * 33);
     uint32_t itile = 0;
     int bias_nt = -1;
@@ -215,6 +216,10 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
             else if (col < p.n_store) bv = p.bias[col];
           }
           s_bias[i] = bv;
+          if (affine) {  // inference: the statistics slots hold the BatchNorm scale / shift of this N tile
+            s_sum[i] = n0 + i < p.n_store ? p.bn_scale[n0 + i] : 0.f;
+            s_sq[i] = n0 + i < p.n_store ? p.bn_shift[n0 + i] : 0.f;
+          }
         }
         named_bar_sync(2, kFpEpiThreads);
         bias_nt = nt;
@@ -250,6 +255,7 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
         for (int j = 0; j < 32; ++j) {
           float x = __uint_as_float(v[j]) + s_bias[chunk * 32 + j];
           if (p.relu) x = fmaxf(x, 0.f);
+          if (affine) x = fmaf(x, s_sum[chunk * 32 + j], s_sq[chunk * 32 + j]);
           f[j] = x;
         }
         if constexpr (sizeof(OutT) == 2) {
@@ -979,6 +985,7 @@ __global__ void __launch_bounds__(kC3Threads, 1)
     const int mrow = q * 32 + lane;
     const int etid = threadIdx.x - 64;
     const bool do_stats = p.stat_sum != nullptr;
+    const bool affine = p.bn_scale != nullptr;
     float* scratch = scratch_all + (warp - 2) * (32 * 33);
     uint32_t it = 0;
     int bias_nt = -1;
@@ -992,8 +999,13 @@ __global__ void __launch_bounds__(kC3Threads, 1)
       const uint32_t acc = it & 1, pacc = (it >> 1) & 1;
       if (nt != bias_nt) {  // (uniform across the epilogue warps) stage this N tile's bias in smem
         named_bar_sync(2, kC3EpiThreads);
-        for (int i = etid; i < BN; i += kC3EpiThreads)
+        for (int i = etid; i < BN; i += kC3EpiThreads) {
           s_bias[i] = (p.bias != nullptr && n0 + i < p.n_store) ? p.bias[n0 + i] : 0.f;
+          if (affine) {  // inference: the statistics slots hold the BatchNorm scale / shift of this N tile
+            s_sum[i] = n0 + i < p.n_store ? p.bn_scale[n0 + i] : 0.f;
+            s_sq[i] = n0 + i < p.n_store ? p.bn_shift[n0 + i] : 0.f;
+          }
+        }
         named_bar_sync(2, kC3EpiThreads);
         bias_nt = nt;
       }
@@ -1018,6 +1030,11 @@ __global__ void __launch_bounds__(kC3Threads, 1)
           float x2 = __uint_as_float(v[4 * jj + 2]) + bb.z, x3 = __uint_as_float(v[4 * jj + 3]) + bb.w;
           if (p.relu) {
             x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+          }
+          if (affine) {
+            const float4 sc = reinterpret_cast<const float4*>(s_sum + chunk * 32)[jj];
+            const float4 sh = reinterpret_cast<const float4*>(s_sq + chunk * 32)[jj];
+            x0 = fmaf(x0, sc.x, sh.x); x1 = fmaf(x1, sc.y, sh.y); x2 = fmaf(x2, sc.z, sh.z); x3 = fmaf(x3, sc.w, sh.w);
           }
           pk[2 * jj] = pack_bf16x2(x0, x1);
           pk[2 * jj + 1] = pack_bf16x2(x2, x3);
@@ -1292,6 +1309,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
     const int mrow = q * 32 + lane;
     const int etid = threadIdx.x - 64;
     const bool do_stats = p.stat_sum != nullptr;
+    const bool affine = p.bn_scale != nullptr;
     uint32_t it = 0;
     int bias_nt = -1;
     for (int t = cluster_id; t < total; t += nclusters, ++it) {
@@ -1304,8 +1322,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
       const uint32_t acc = it & 1, pacc = (it >> 1) & 1;
       if (nt != bias_nt) {
         named_bar_sync(2, kC3EpiThreads);
-        for (int i = etid; i < BN; i += kC3EpiThreads)
+        for (int i = etid; i < BN; i += kC3EpiThreads) {
           s_bias[i] = (p.bias != nullptr && n0 + i < p.n_store) ? p.bias[n0 + i] : 0.f;
+          if (affine) {  // inference: the statistics slots hold the BatchNorm scale / shift of this N tile
+            s_sum[i] = n0 + i < p.n_store ? p.bn_scale[n0 + i] : 0.f;
+            s_sq[i] = n0 + i < p.n_store ? p.bn_shift[n0 + i] : 0.f;
+          }
+        }
         named_bar_sync(2, kC3EpiThreads);
         bias_nt = nt;
       }
@@ -1330,6 +1353,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
           float x2 = __uint_as_float(v[4 * jj + 2]) + bb.z, x3 = __uint_as_float(v[4 * jj + 3]) + bb.w;
           if (p.relu) {
             x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f);
+          }
+          if (affine) {
+            const float4 sc = reinterpret_cast<const float4*>(s_sum + chunk * 32)[jj];
+            const float4 sh = reinterpret_cast<const float4*>(s_sq + chunk * 32)[jj];
+            x0 = fmaf(x0, sc.x, sh.x); x1 = fmaf(x1, sc.y, sh.y); x2 = fmaf(x2, sc.z, sh.z); x3 = fmaf(x3, sc.w, sh.w);
           }
           pk[2 * jj] = pack_bf16x2(x0, x1);
           pk[2 * jj + 1] = pack_bf16x2(x2, x3);

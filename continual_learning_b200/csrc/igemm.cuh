@@ -48,6 +48,8 @@ struct FpropParams {
   int relu;
   double* stat_sum;    // per-column sum / sum of squares of the stored values; may be null
   double* stat_sq;
+  const float* bn_scale;  // inference: out = relu(acc + bias) * bn_scale + bn_shift (stat_* must then be null)
+  const float* bn_shift;
 };
 
 struct WgradParams {
@@ -109,6 +111,8 @@ struct Conv3Params {
   int relu;
   double* stat_sum;
   double* stat_sq;
+  const float* bn_scale;  // inference epilogue, see FpropParams
+  const float* bn_shift;
 };
 // CTA-pair variant (tcgen05.mma.cta_group::2, M = 256): a0/a1 box {64, 16, 18}, b box {64, BN/2, 1}
 cudaError_t launch_conv3x2(int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,

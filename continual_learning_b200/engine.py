@@ -64,6 +64,7 @@ class UNetEngine:
         self.fuse_bn = False     # finalize folded into the apply kernels: measured 0.17 ms/step SLOWER (fp64 prologue per block)
         self.side_pack = True    # late-layer weight packing on the side stream
         self.training_fwd = True
+        self.save_for_backward = True
         self.logits = None
 
     # ------------------------------------------------------------------ persistent buffers
@@ -250,6 +251,22 @@ class UNetEngine:
     def _unit_fwd(self, u, x0, x1, training, pool=False):
         n, h, w = x0.shape[0], x0.shape[1], x0.shape[2]
         u.x0, u.x1 = x0, x1
+        if not training and not self.save_for_backward:
+            # inference: BatchNorm with running statistics is an affine map known before the conv runs ->
+            # applied in the conv epilogue, no pre-BN tensor and no separate BN pass
+            bn = u.bn
+            ops.bn_finalize(u.s_sum, u.s_sq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                            u.vec[0], u.vec[1], u.vec[2], u.vec[3], n * h * w, eps=bn.eps, momentum=0.0,
+                            training=False)
+            bias = u.conv.bias.detach()
+            if u.stem:
+                u.z = ops.gemm_fprop_eval(x0, u.wf, bias, u.cout, u.vec[2], u.vec[3], relu=True)
+            else:
+                u.z = ops.conv3x3_fprop_eval(x0, x1, u.wf, bias, u.vec[2], u.vec[3], relu=True)
+            u.y, u.pooled, u.idx = None, None, None
+            if pool:
+                _, u.pooled, u.idx = ops.bn_apply_pool(u.z, None, None)
+            return u.z
         stats = (u.s_sum, u.s_sq) if training else None
         bias = u.conv.bias.detach()
         if u.stem:
@@ -273,8 +290,10 @@ class UNetEngine:
             pool=pool)
         return u.z
 
-    def forward(self, x, training=True):
-        """x: fp32 NCHW CUDA tensor. Returns fp32 logits [N, H, W, num_classes] (NHWC memory)."""
+    def forward(self, x, training=True, save_for_backward=True):
+        """x: fp32 NCHW CUDA tensor. Returns fp32 logits [N, H, W, num_classes] (NHWC memory).
+        save_for_backward=False (with training=False) selects the fused inference kernels."""
+        self.save_for_backward = save_for_backward
         if not x.is_cuda:
             raise RuntimeError("continual_learning_b200.UNet runs on CUDA (sm_100a) only: there is no CPU fallback")
         _lib.ensure_device(x.device.index)
@@ -401,6 +420,9 @@ class UNetEngine:
         data-parallel caller can start reducing them while the encoder backward still runs."""
         U = self.units
         nc = self.m.num_classes
+        if not self.save_for_backward:
+            raise RuntimeError("backward() after an inference forward (save_for_backward=False): the fused "
+                               "conv+BatchNorm kernels keep no pre-BN activations")
         self.acc_b.zero_()
         self.Gp.zero_()
         # 1x1 head (models/unet.py:72)

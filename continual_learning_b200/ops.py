@@ -104,6 +104,17 @@ def conv3x3_fprop(x0, x1, wf, bias, relu=True, stats=None, out=None):
     return y
 
 
+def conv3x3_fprop_eval(x0, x1, wf, bias, scale, shift, relu=True, out=None):
+    """inference: z = relu(conv(x) + bias) * scale + shift in one launch (BatchNorm with running statistics)."""
+    _dev(x0)
+    n, h, w, c0 = x0.shape
+    c1 = 0 if x1 is None else x1.shape[3]
+    cout = wf.shape[1]
+    z = torch.empty((n, h, w, cout), device=x0.device, dtype=bf16) if out is None else out
+    _lib.call("clk_conv3x3_fprop_eval", x0, c0, x1, c1, wf, bias, z, scale, shift, n, h, w, cout, 1 if relu else 0)
+    return z
+
+
 def conv3x3_dgrad(dy, wd, c0, c1=0, out0=None, out1=None):
     _dev(dy)
     n, h, w, cout = dy.shape
@@ -160,6 +171,18 @@ def gemm_fprop(a, w, bias, n_store, out_f32=False, relu=False, stats=None, out=N
     s_sum, s_sq = (None, None) if stats is None else stats
     _lib.call("clk_gemm_fprop", a, k, w, bias, out, ldo, n_store, 1 if out_f32 else 0, 1 if relu else 0, s_sum,
               s_sq, p, npad)
+    return out
+
+
+def gemm_fprop_eval(a, w, bias, n_store, scale, shift, relu=True, out=None):
+    """inference form of gemm_fprop (bf16 output): relu(a w^T + bias) * scale + shift."""
+    _dev(a)
+    k = a.shape[-1]
+    p = a.numel() // k
+    if out is None:
+        out = torch.empty((*a.shape[:-1], n_store), device=a.device, dtype=bf16)
+    _lib.call("clk_gemm_fprop_eval", a, k, w, bias, out, out.shape[-1], n_store, 1 if relu else 0, scale, shift, p,
+              w.shape[0])
     return out
 
 

@@ -36,7 +36,7 @@ class TrainStep:
         old_logits = None
         if self.old is not None:
             oeng = self.old.engine
-            old_logits = oeng.forward(x, training=False)
+            old_logits = oeng.forward(x, training=False, save_for_backward=False)
             oeng.release()
         logits = eng.forward(x, training=self.model.training)
         self.loss_acc.zero_()

@@ -94,7 +94,7 @@ class UNet(nn.Module):
         eng = self.engine
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return _UNetFn.apply(x, eng, self.training, *self.parameters())
-        logits = eng.forward(x, training=self.training)
+        logits = eng.forward(x, training=self.training, save_for_backward=False)
         out = logits.permute(0, 3, 1, 2)
         return out
 

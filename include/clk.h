@@ -80,6 +80,13 @@ int clk_reduce_partials_multi(const void* jobs, int njobs, int total_blocks, clk
 int clk_conv3x3_fprop(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias,
                       void* y, double* stat_sum, double* stat_sq, int N, int H, int W, int Cout, int relu,
                       clk_stream_t st);
+/* Inference form (module.eval(), trainer.py:271, and the frozen old model of the continual step): BatchNorm with
+ * running statistics is a per-channel affine map known before the conv runs, so it is applied in the epilogue:
+ * z = relu(conv(x) + bias) * bn_scale + bn_shift, one launch, no intermediate tensor.  bn_scale / bn_shift: f32[Cout]
+ * from clk_bn_finalize(training = 0). */
+int clk_conv3x3_fprop_eval(const void* x0, int C0, const void* x1, int C1, const void* w, const float* bias,
+                           void* z, const float* bn_scale, const float* bn_shift, int N, int H, int W, int Cout,
+                           int relu, clk_stream_t st);
 /* dgrad of the same conv (autograd of trainer.py:175): dy bf16 [N][H][W][Cout],
  * wd bf16 [9][C0+C1][Cout] (clk_pack_w outBA, rev=1); writes dx0 [..][C0] and dx1 [..][C1]. */
 int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C0, void* dx1, int C1,
@@ -100,6 +107,10 @@ int clk_conv3x3_wgrad_split(const void* dy, int Cout, const void* x0, int C0, co
 int clk_gemm_fprop(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
                    int out_is_f32, int relu, double* stat_sum, double* stat_sq, long long P, int Npad,
                    clk_stream_t st);
+/* inference form of the stem (bf16 output): out = relu(a * w^T + bias) * bn_scale + bn_shift */
+int clk_gemm_fprop_eval(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
+                        int relu, const float* bn_scale, const float* bn_shift, long long P, int Npad,
+                        clk_stream_t st);
 /* out fp32 [ld_u][ld_t] += u[P][CU]^T * t[P][CT]  (weight gradient of the GEMMs above) */
 int clk_gemm_wgrad(const void* u, int CU, const void* t, int CT, float* out, int ld_u, int ld_t,
                    long long P, clk_stream_t st);

@@ -85,6 +85,13 @@ def test_forward_matches_reference_golden(clk, golden_dir, name, seed_w, seed_x,
     sd_now = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     ref = UNetRef(sd_now, nc, training=False)(x)
     assert rel(ev, ref) <= 3e-2
+    # with autograd enabled the eval forward keeps the pre-BN tensors (conv, BN as separate launches); under no_grad
+    # BatchNorm is folded into the conv epilogue: same function, one bf16 rounding less per unit
+    ev_grad = m(x.cuda())
+    assert ev_grad.requires_grad and rel(ev_grad, ev) <= 1e-2
+    with pytest.raises(RuntimeError, match="inference"):
+        m.engine.forward(x.cuda(), training=False, save_for_backward=False)
+        m.engine.backward(torch.zeros(b, h, w, 64, device="cuda", dtype=torch.bfloat16))
 
 
 def test_train_step_gradients_vs_fp32_and_matched_oracle(clk):

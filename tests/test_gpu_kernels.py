@@ -95,6 +95,36 @@ def test_conv3x3_fprop_with_folded_concat(ops, conv_kernel, n, h, w, c0, c1, co)
     assert rel(s_sum, q.sum(0)) <= 1e-6 and rel(s_sq, (q * q).sum(0)) <= 1e-6
 
 
+@pytest.mark.parametrize("n,h,w,c0,c1,co", [(2, 16, 16, 64, 0, 64), (3, 8, 24, 128, 0, 256), (2, 16, 16, 64, 64, 128),
+                                              (2, 3, 5, 64, 64, 64), (1, 34, 18, 128, 0, 512)])
+def test_conv3x3_fprop_eval_applies_running_stat_batchnorm_in_the_epilogue(ops, conv_kernel, n, h, w, c0, c1, co):
+    """module.eval() path (trainer.py:271): conv -> ReLU -> BatchNorm(running stats) in ONE launch against the three
+    stock ops in fp32."""
+    g = gen(n * 10 + h + co + 5)
+    x, wt, b = bfr(rnd(g, n, c0 + c1, h, w)), rnd(g, co, c0 + c1, 3, 3, scale=0.05), rnd(g, co)
+    gamma, beta = rnd(g, co), rnd(g, co)
+    rmean, rvar = rnd(g, co, scale=0.3), torch.rand(co, generator=g) + 0.5
+    scale = gamma / torch.sqrt(rvar + 1e-5)
+    shift = beta - rmean * scale
+    xh = to_nhwc_dev(x)
+    x0 = xh[..., :c0].contiguous()
+    x1 = xh[..., c0:].contiguous() if c1 else None
+    wf, _ = ops.pack_conv3x3(wt.cuda())
+    z = ops.conv3x3_fprop_eval(x0, x1, wf, b.cuda(), scale.cuda(), shift.cuda(), relu=True)
+    ref = F.batch_norm(torch.relu(F.conv2d(x, bfr(wt), b, padding=1)), rmean, rvar, gamma, beta, training=False)
+    assert rel(from_nhwc(z), ref) <= BF16_TOL
+
+
+def test_gemm_fprop_eval_stem(ops):
+    g = gen(77)
+    P, K, N = 1000, 64, 64
+    a, w, b = bfr(rnd(g, P, K)), bfr(rnd(g, N, K, scale=0.1)), rnd(g, N)
+    scale, shift = rnd(g, N), rnd(g, N)
+    out = ops.gemm_fprop_eval(a.to(torch.bfloat16).cuda(), w.to(torch.bfloat16).cuda(), b.cuda(), N, scale.cuda(),
+                              shift.cuda(), relu=True)
+    assert rel(out, torch.relu(a @ w.t() + b) * scale + shift) <= BF16_TOL
+
+
 @pytest.mark.parametrize("n,h,w,c0,c1,co", [(2, 16, 16, 64, 0, 64), (2, 8, 8, 128, 128, 128), (1, 16, 16, 256, 0, 64),
                                               (2, 6, 10, 64, 64, 64), (1, 64, 48, 128, 0, 64), (2, 33, 17, 64, 64, 128)])
 def test_conv3x3_dgrad_split_destinations(ops, conv_kernel, n, h, w, c0, c1, co):
