@@ -209,6 +209,14 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
       if (nt != bias_nt) {
         named_bar_sync(2, kFpEpiThreads);
         for (int i = etid; i < BN; i += kFpEpiThreads) {
+          if (do_stats && bias_nt >= 0) {  // flush the statistics of the N tile this CTA just left
+            if (bias_nt * BN + i < p.n_store) {
+              atomicAdd(&p.stat_sum[bias_nt * BN + i], static_cast<double>(s_sum[i]));
+              atomicAdd(&p.stat_sq[bias_nt * BN + i], static_cast<double>(s_sq[i]));
+            }
+            s_sum[i] = 0.f;
+            s_sq[i] = 0.f;
+          }
           float bv = 0.f;
           if (p.bias != nullptr) {
             const int col = n0 + i;
@@ -316,17 +324,15 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (do_stats) {
-        named_bar_sync(1, kFpEpiThreads);
-        for (int i = etid; i < BN; i += kFpEpiThreads) {
-          if (n0 + i < p.n_store) {
-            atomicAdd(&p.stat_sum[n0 + i], static_cast<double>(s_sum[i]));
-            atomicAdd(&p.stat_sq[n0 + i], static_cast<double>(s_sq[i]));
-          }
-          s_sum[i] = 0.f;
-          s_sq[i] = 0.f;
+    }
+    // statistics stay in shared memory across the tiles of one N tile: one fp64 atomic per channel per CTA and N tile
+    if (do_stats && bias_nt >= 0) {
+      named_bar_sync(1, kFpEpiThreads);
+      for (int i = etid; i < BN; i += kFpEpiThreads) {
+        if (bias_nt * BN + i < p.n_store) {
+          atomicAdd(&p.stat_sum[bias_nt * BN + i], static_cast<double>(s_sum[i]));
+          atomicAdd(&p.stat_sq[bias_nt * BN + i], static_cast<double>(s_sq[i]));
         }
-        named_bar_sync(1, kFpEpiThreads);
       }
     }
   }
@@ -1000,6 +1006,14 @@ __global__ void __launch_bounds__(kC3Threads, 1)
       if (nt != bias_nt) {  // (uniform across the epilogue warps) stage this N tile's bias in smem
         named_bar_sync(2, kC3EpiThreads);
         for (int i = etid; i < BN; i += kC3EpiThreads) {
+          if (do_stats && bias_nt >= 0) {  // flush the statistics of the N tile this CTA just left
+            if (bias_nt * BN + i < p.n_store) {
+              atomicAdd(&p.stat_sum[bias_nt * BN + i], static_cast<double>(s_sum[i]));
+              atomicAdd(&p.stat_sq[bias_nt * BN + i], static_cast<double>(s_sq[i]));
+            }
+            s_sum[i] = 0.f;
+            s_sq[i] = 0.f;
+          }
           s_bias[i] = (p.bias != nullptr && n0 + i < p.n_store) ? p.bias[n0 + i] : 0.f;
           if (affine) {  // inference: the statistics slots hold the BatchNorm scale / shift of this N tile
             s_sum[i] = n0 + i < p.n_store ? p.bn_scale[n0 + i] : 0.f;
@@ -1072,17 +1086,15 @@ __global__ void __launch_bounds__(kC3Threads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (do_stats) {
-        named_bar_sync(1, kC3EpiThreads);
-        for (int i = etid; i < BN; i += kC3EpiThreads) {
-          if (n0 + i < p.n_store) {
-            atomicAdd(&p.stat_sum[n0 + i], static_cast<double>(s_sum[i]));
-            atomicAdd(&p.stat_sq[n0 + i], static_cast<double>(s_sq[i]));
-          }
-          s_sum[i] = 0.f;
-          s_sq[i] = 0.f;
+    }
+    // statistics stay in shared memory across the tiles of one N tile: one fp64 atomic per channel per CTA and N tile
+    if (do_stats && bias_nt >= 0) {
+      named_bar_sync(1, kC3EpiThreads);
+      for (int i = etid; i < BN; i += kC3EpiThreads) {
+        if (bias_nt * BN + i < p.n_store) {
+          atomicAdd(&p.stat_sum[bias_nt * BN + i], static_cast<double>(s_sum[i]));
+          atomicAdd(&p.stat_sq[bias_nt * BN + i], static_cast<double>(s_sq[i]));
         }
-        named_bar_sync(1, kC3EpiThreads);
       }
     }
   }
@@ -1323,6 +1335,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
       if (nt != bias_nt) {
         named_bar_sync(2, kC3EpiThreads);
         for (int i = etid; i < BN; i += kC3EpiThreads) {
+          if (do_stats && bias_nt >= 0) {  // flush the statistics of the N tile this CTA just left
+            if (bias_nt * BN + i < p.n_store) {
+              atomicAdd(&p.stat_sum[bias_nt * BN + i], static_cast<double>(s_sum[i]));
+              atomicAdd(&p.stat_sq[bias_nt * BN + i], static_cast<double>(s_sq[i]));
+            }
+            s_sum[i] = 0.f;
+            s_sq[i] = 0.f;
+          }
           s_bias[i] = (p.bias != nullptr && n0 + i < p.n_store) ? p.bias[n0 + i] : 0.f;
           if (affine) {  // inference: the statistics slots hold the BatchNorm scale / shift of this N tile
             s_sum[i] = n0 + i < p.n_store ? p.bn_scale[n0 + i] : 0.f;
@@ -1392,17 +1412,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
-      if (do_stats) {
-        named_bar_sync(1, kC3EpiThreads);
-        for (int i = etid; i < BN; i += kC3EpiThreads) {
-          if (n0 + i < p.n_store) {
-            atomicAdd(&p.stat_sum[n0 + i], static_cast<double>(s_sum[i]));
-            atomicAdd(&p.stat_sq[n0 + i], static_cast<double>(s_sq[i]));
-          }
-          s_sum[i] = 0.f;
-          s_sq[i] = 0.f;
+    }
+    // statistics stay in shared memory across the tiles of one N tile: one fp64 atomic per channel per CTA and N tile
+    if (do_stats && bias_nt >= 0) {
+      named_bar_sync(1, kC3EpiThreads);
+      for (int i = etid; i < BN; i += kC3EpiThreads) {
+        if (bias_nt * BN + i < p.n_store) {
+          atomicAdd(&p.stat_sum[bias_nt * BN + i], static_cast<double>(s_sum[i]));
+          atomicAdd(&p.stat_sq[bias_nt * BN + i], static_cast<double>(s_sq[i]));
         }
-        named_bar_sync(1, kC3EpiThreads);
       }
     }
   }
