@@ -10,6 +10,9 @@
 #include "igemm.cuh"
 #include "membound.cuh"
 
+namespace clk {
+int g_pdl = 1;  // programmatic dependent launch for every kernel of the library (clk_ptx.cuh)
+}
 using namespace clk;
 
 namespace {
@@ -230,6 +233,8 @@ int clk_set_tuning(const char* key, int value) {
   else if (strcmp(key, "conv3_v2") == 0) g_conv3_v2 = value;
   else if (strcmp(key, "conv3_min_hw") == 0) g_conv3_min_hw = value;
   else if (strcmp(key, "conv3_pair") == 0) g_conv3_pair = value;
+  else if (strcmp(key, "pdl") == 0) g_pdl = value ? 1 : 0;
+  else if (strcmp(key, "pdl_tensor_trigger") == 0) return cuda_status(igemm_set_pdl_mode(value), "pdl_tensor_trigger");
   else return fail(CLK_E_BADARG, "unknown tuning key %s", key);
   return CLK_OK;
 }

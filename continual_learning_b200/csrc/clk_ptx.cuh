@@ -279,4 +279,30 @@ __device__ __forceinline__ float warp_colsum32(float (&f)[32], int lane) {
   return f[0];
 }
 
+// ---- programmatic dependent launch (PDL): every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, lets its successor be scheduled as early as possible
+// (pdl_launch_dependents at the top) and waits for the complete predecessor grid, memory flushed, before its first
+// dependent global access (pdl_wait).  The successor's launch latency and prologue (barrier init, TMEM allocation,
+// descriptor prefetch) then overlap the predecessor's tail.  Both instructions are no-ops in a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_pdl;  // api.cu, tuning key "pdl"
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace clk

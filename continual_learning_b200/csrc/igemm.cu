@@ -17,6 +17,10 @@ constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 static int g_fprop_sms = 148;
 void igemm_set_num_sms(int n) { g_fprop_sms = n > 0 ? n : 148; }
+// when a tensor-core kernel lets its successor be scheduled (PDL): 0 = at its very start, 1 = when a CTA's TMA producer
+// has issued its last load (the successor's prologue overlaps the last tile's MMAs + epilogue), 2 = implicit at exit
+__device__ int d_pdl_mode = 1;
+cudaError_t igemm_set_pdl_mode(int mode) { return cudaMemcpyToSymbol(d_pdl_mode, &mode, sizeof(int)); }
 
 // ------------------------------------------------------------------------------------------
 // tile -> TMA base coordinates (coords 1..4; coord 0 is always the channel)
@@ -96,6 +100,7 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
   constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
   constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;
 
+  if (d_pdl_mode == 0) pdl_launch_dependents();  // the next kernel of the stream may be scheduled and run its prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sA = smem;
@@ -139,6 +144,7 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // predecessor grid complete and flushed: inputs may be read, outputs written
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -164,6 +170,7 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
       }
     }
     __syncwarp();
+    if (d_pdl_mode == 1) pdl_launch_dependents();  // this CTA has requested its last operand tile
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer (single thread)
     if (elect_one()) {
@@ -357,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   constexpr int NBS = BN / 64;  // T slabs per tap
   const int stage_bytes = (2 + p.G * NBS) * kWgSlab;
 
+  if (d_pdl_mode == 0) pdl_launch_dependents();  // the next kernel of the stream may be scheduled and run its prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + stages * stage_bytes);
@@ -401,6 +409,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // predecessor grid complete and flushed: inputs may be read, outputs written
 
   if (warp == 0) {
     if (elect_one()) {
@@ -440,6 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
     __syncwarp();
+    if (d_pdl_mode == 1) pdl_launch_dependents();  // this CTA has requested its last operand tile
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 1, 1);
@@ -518,6 +528,7 @@ constexpr int kW9StageBytes = kW9UBytes + kW9TBytes;
 __global__ void __launch_bounds__(kThreads, 1)
     igemm_wgrad9_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT0,
                         const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ Wgrad9Params p) {
+  if (d_pdl_mode == 0) pdl_launch_dependents();  // the next kernel of the stream may be scheduled and run its prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kW9Stages * kW9StageBytes);
@@ -554,6 +565,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // predecessor grid complete and flushed: inputs may be read, outputs written
 
   if (warp == 0) {
     if (elect_one()) {
@@ -576,6 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
     __syncwarp();
+    if (d_pdl_mode == 1) pdl_launch_dependents();  // this CTA has requested its last operand tile
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
@@ -649,7 +662,7 @@ cudaError_t launch_wgrad9(const CUtensorMap& u, const CUtensorMap& t0, const CUt
     attr_done = true;
   }
   dim3 grid(p.cin_slabs * p.cout_tiles, p.ksplit);
-  igemm_wgrad9_kernel<<<grid, kThreads, smem, st>>>(u, t0, t1, p);
+  launch_k(igemm_wgrad9_kernel, dim3(grid), dim3(kThreads), smem, st, u, t0, t1, p);
   return cudaGetLastError();
 }
 
@@ -669,6 +682,7 @@ constexpr int kW2StageBytes = kW9UBytes + kW9TBytes;  // [128 px][64 cout] + [18
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
     igemm_wgrad9x2_kernel(const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapT0,
                           const __grid_constant__ CUtensorMap mapT1, const __grid_constant__ Wgrad9Params p) {
+  if (d_pdl_mode == 0) pdl_launch_dependents();  // the next kernel of the stream may be scheduled and run its prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   // 2 KB pad after the last stage: CTA 1's unused tap slots read one halo row past their tile
@@ -710,6 +724,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // predecessor grid complete and flushed: inputs may be read, outputs written
 
   if (warp == 0) {
     if (elect_one()) {
@@ -733,6 +748,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       }
     }
     __syncwarp();
+    if (d_pdl_mode == 1) pdl_launch_dependents();  // this CTA has requested its last operand tile
   } else if (warp == 1) {
     if (leader && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, 128, 1, 1);
@@ -810,7 +826,7 @@ cudaError_t launch_wgrad9x2(const CUtensorMap& u, const CUtensorMap& t0, const C
     attr_done = true;
   }
   dim3 grid(2 * p.cin_slabs * p.cout_tiles, p.ksplit);  // cout_tiles = Cout / 128 here
-  igemm_wgrad9x2_kernel<<<grid, kThreads, smem, st>>>(u, t0, t1, p);
+  launch_k(igemm_wgrad9x2_kernel, dim3(grid), dim3(kThreads), smem, st, u, t0, t1, p);
   return cudaGetLastError();
 }
 
@@ -842,6 +858,7 @@ __global__ void __launch_bounds__(kC3Threads, 1)
   constexpr int B_BYTES = C3Cfg<BN>::BBytes;
   constexpr uint32_t TMEM_COLS = 4 * BN;
 
+  if (d_pdl_mode == 0) pdl_launch_dependents();  // the next kernel of the stream may be scheduled and run its prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sA = smem;
@@ -888,6 +905,7 @@ __global__ void __launch_bounds__(kC3Threads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // predecessor grid complete and flushed: inputs may be read, outputs written
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer
@@ -942,6 +960,7 @@ __global__ void __launch_bounds__(kC3Threads, 1)
       }
     }
     __syncwarp();
+    if (d_pdl_mode == 1) pdl_launch_dependents();  // this CTA has requested its last operand tile
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer
     if (elect_one()) {
@@ -1116,7 +1135,7 @@ static cudaError_t launch_conv3_t(const CUtensorMap& a0, const CUtensorMap& a1, 
   }
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms) grid = num_sms;
-  igemm_conv3_kernel<BN><<<grid, kC3Threads, smem, st>>>(a0, a1, b, p);
+  launch_k(igemm_conv3_kernel<BN>, dim3(grid), dim3(kC3Threads), smem, st, a0, a1, b, p);
   return cudaGetLastError();
 }
 
@@ -1162,6 +1181,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
   constexpr int PITCH = Cfg::PitchPx;       // pixels
   constexpr int TILE_W = 8 * SUB;           // output columns owned by one CTA
 
+  if (d_pdl_mode == 0) pdl_launch_dependents();  // the next kernel of the stream may be scheduled and run its prologue
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sA = smem;
@@ -1214,6 +1234,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
   cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / cross-CTA TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // predecessor grid complete and flushed: inputs may be read, outputs written
 
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (one per CTA)
@@ -1267,6 +1288,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
       }
     }
     __syncwarp();
+    if (d_pdl_mode == 1) pdl_launch_dependents();  // this CTA has requested its last operand tile
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer: leader CTA only
     if (leader && elect_one()) {
@@ -1444,7 +1466,7 @@ static cudaError_t launch_conv3x2_t(const CUtensorMap& a0, const CUtensorMap& a1
   }
   int clusters = p.m_tiles * p.n_tiles;
   if (clusters > num_sms / 2) clusters = num_sms / 2;
-  igemm_conv3x2_kernel<BN, SUB><<<2 * clusters, kC3Threads, smem, st>>>(a0, a1, b, p);
+  launch_k(igemm_conv3x2_kernel<BN, SUB>, dim3(2 * clusters), dim3(kC3Threads), smem, st, a0, a1, b, p);
   return cudaGetLastError();
 }
 
@@ -1480,7 +1502,7 @@ static cudaError_t launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1,
   int grid = m_tiles * n_tiles;
   const int cap = g_fprop_sms * (smem <= 113 * 1024 ? 2 : 1);  // resident CTAs per SM by shared memory
   if (grid > cap) grid = cap;
-  igemm_fprop_kernel<BN, STAGES, OutT><<<grid, kFpThreads, smem, st>>>(a0, a1, b, p, m_tiles, n_tiles);
+  launch_k(igemm_fprop_kernel<BN, STAGES, OutT>, dim3(grid), dim3(kFpThreads), smem, st, a0, a1, b, p, m_tiles, n_tiles);
   return cudaGetLastError();
 }
 
@@ -1518,7 +1540,7 @@ static cudaError_t launch_wgrad_t(const CUtensorMap& u, const CUtensorMap& t0,
     attr_done = true;
   }
   dim3 grid(p.m_tiles * p.n_tiles * p.tap_groups, p.ksplit);
-  igemm_wgrad_kernel<BN><<<grid, kThreads, smem, st>>>(u, t0, t1, p, stages, cols);
+  launch_k(igemm_wgrad_kernel<BN>, dim3(grid), dim3(kThreads), smem, st, u, t0, t1, p, stages, cols);
   return cudaGetLastError();
 }
 

@@ -67,6 +67,7 @@ struct WgradParams {
 };
 
 void igemm_set_num_sms(int n);
+cudaError_t igemm_set_pdl_mode(int mode);
 
 // Launchers (igemm.cu). Return cudaError_t from the launch; maps are built by the caller.
 cudaError_t launch_fprop(int BN, int out_is_f32, const CUtensorMap& a0, const CUtensorMap& a1,

@@ -10,6 +10,7 @@
 // argmax/eq-count trainer.py:183-184; metrics._fast_conf_matrix metrics.py:32-38; optim.Adam
 // trainer.py:108-110,176.
 #include "membound.cuh"
+#include "clk_ptx.cuh"
 
 #include <cuda_bf16.h>
 #include <math_constants.h>
@@ -52,6 +53,8 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 // layout conversion
 __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                              int N, int C, int HW, int Cpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   // one thread per (n, pixel); channels are few in the use cases (stem input, logits)
   const long long total = static_cast<long long>(N) * HW;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -65,6 +68,8 @@ __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_b
 }
 __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y,
                                              int N, int C, int HW, int ldc) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   // grid: (ceil(HW/32), ceil(C/32), N); transposes a 32 pixel x 32 channel tile
   const int n = blockIdx.z;
@@ -82,6 +87,8 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x
 }
 __global__ void nhwc_f32_to_nchw_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int N,
                                             int C, int HW, int ldc) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -99,7 +106,7 @@ __global__ void nhwc_f32_to_nchw_f32_kernel(const float* __restrict__ x, float* 
 cudaError_t nchw_f32_to_nhwc_bf16(const float* x, void* y, int N, int C, int H, int W, int Cpad,
                                   cudaStream_t st) {
   const long long total = static_cast<long long>(N) * H * W;
-  nchw_f32_to_nhwc_bf16_kernel<<<grid_for(total, 256), 256, 0, st>>>(
+  launch_k(nchw_f32_to_nhwc_bf16_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, 
       x, static_cast<__nv_bfloat16*>(y), N, C, H * W, Cpad);
   return cudaGetLastError();
 }
@@ -107,9 +114,9 @@ cudaError_t nhwc_to_nchw_f32(const void* x, int x_is_f32, float* y, int N, int C
                              int ldc, cudaStream_t st) {
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, N), block(32, 8);
   if (x_is_f32)
-    nhwc_f32_to_nchw_f32_kernel<<<grid, block, 0, st>>>(static_cast<const float*>(x), y, N, C, H * W, ldc);
+    launch_k(nhwc_f32_to_nchw_f32_kernel, dim3(grid), dim3(block), 0, st, static_cast<const float*>(x), y, N, C, H * W, ldc);
   else
-    nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(x), y, N, C,
+    launch_k(nhwc_bf16_to_nchw_f32_kernel, dim3(grid), dim3(block), 0, st, static_cast<const __nv_bfloat16*>(x), y, N, C,
                                                          H * W, ldc);
   return cudaGetLastError();
 }
@@ -118,6 +125,8 @@ cudaError_t nhwc_to_nchw_f32(const void* x, int x_is_f32, float* y, int N, int C
 // stem im2col: x NCHW fp32 [N,Cin,H,W] -> A [N*H*W][64] bf16, k = c*9 + r*3 + s (zero padded)
 __global__ void im2col3x3_stem_kernel(const float* __restrict__ x, uint4* __restrict__ a, int N, int Cin,
                                       int H, int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(N) * H * W;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -154,6 +163,8 @@ __global__ void im2col3x3_stem_kernel(const float* __restrict__ x, uint4* __rest
 // Cin == 3 specialisation keeps everything in registers (fully unrolled indices)
 __global__ void im2col3x3_stem3_kernel(const float* __restrict__ x, uint4* __restrict__ a, int N, int H,
                                        int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(N) * H * W;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -193,9 +204,9 @@ __global__ void im2col3x3_stem3_kernel(const float* __restrict__ x, uint4* __res
 cudaError_t im2col3x3_stem(const float* x, void* a, int N, int Cin, int H, int W, cudaStream_t st) {
   const long long total = static_cast<long long>(N) * H * W;
   if (Cin == 3)
-    im2col3x3_stem3_kernel<<<grid_for(total, 256, 16), 256, 0, st>>>(x, static_cast<uint4*>(a), N, H, W);
+    launch_k(im2col3x3_stem3_kernel, dim3(grid_for(total, 256, 16)), dim3(256), 0, st, x, static_cast<uint4*>(a), N, H, W);
   else
-    im2col3x3_stem_kernel<<<grid_for(total, 128, 16), 128, 0, st>>>(x, static_cast<uint4*>(a), N, Cin, H, W);
+    launch_k(im2col3x3_stem_kernel, dim3(grid_for(total, 128, 16)), dim3(128), 0, st, x, static_cast<uint4*>(a), N, Cin, H, W);
   return cudaGetLastError();
 }
 
@@ -205,6 +216,8 @@ cudaError_t im2col3x3_stem(const float* x, void* a, int N, int Cin, int H, int W
 __global__ void pack_w_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ outAB,
                               __nv_bfloat16* __restrict__ outBA, int A, int B, int T, int ldA, int ldB,
                               int ldB2, int ldA2, int rev) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float tile[];  // [T][32][33]
   const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
   const int tid = threadIdx.x;  // 256 threads
@@ -234,7 +247,7 @@ cudaError_t pack_w(const float* src, void* outAB, void* outBA, int A, int B, int
                    int ldB2, int ldA2, int rev, cudaStream_t st) {
   dim3 grid((B + 31) / 32, (A + 31) / 32);
   const size_t smem = static_cast<size_t>(T) * 32 * 33 * sizeof(float);
-  pack_w_kernel<<<grid, 256, smem, st>>>(src, static_cast<__nv_bfloat16*>(outAB),
+  launch_k(pack_w_kernel, dim3(grid), dim3(256), smem, st, src, static_cast<__nv_bfloat16*>(outAB),
                                          static_cast<__nv_bfloat16*>(outBA), A, B, T, ldA, ldB, ldB2, ldA2,
                                          rev);
   return cudaGetLastError();
@@ -243,6 +256,8 @@ cudaError_t pack_w(const float* src, void* outAB, void* outBA, int A, int B, int
 // packed fp32 gradient D[T][ldA][ldB] -> grad[A][B][T] (dst = alpha*D, or dst += alpha*D)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ D, float* __restrict__ grad, int A, int B,
                                     int T, int ldA, int ldB, float alpha, int accumulate, int transposed) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float tile[];  // [32 a][32*T + 1]
   const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
   const int pitch = 32 * T + 1;
@@ -274,7 +289,7 @@ cudaError_t unpack_wgrad(const float* D, float* grad, int A, int B, int T, int l
                          int accumulate, int transposed, cudaStream_t st) {
   dim3 grid((B + 31) / 32, (A + 31) / 32);
   const size_t smem = static_cast<size_t>(32) * (32 * T + 1) * sizeof(float);
-  unpack_wgrad_kernel<<<grid, 256, smem, st>>>(D, grad, A, B, T, ldA, ldB, alpha, accumulate, transposed);
+  launch_k(unpack_wgrad_kernel, dim3(grid), dim3(256), smem, st, D, grad, A, B, T, ldA, ldB, alpha, accumulate, transposed);
   return cudaGetLastError();
 }
 
@@ -286,6 +301,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                    float* __restrict__ scale, float* __restrict__ shift, int C,
                                    double count, float eps, float momentum, int training) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, invstd;
@@ -314,7 +331,7 @@ cudaError_t bn_finalize(const double* sum, const double* sq, const float* gamma,
                         float* running_mean, float* running_var, float* mean_out, float* invstd_out,
                         float* scale, float* shift, int C, double count, float eps, float momentum,
                         int training, cudaStream_t st) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sum, sq, gamma, beta, running_mean, running_var,
+  launch_k(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, st, sum, sq, gamma, beta, running_mean, running_var,
                                                       mean_out, invstd_out, scale, shift, C, count, eps,
                                                       momentum, training);
   return cudaGetLastError();
@@ -325,6 +342,8 @@ cudaError_t bn_finalize(const double* sum, const double* sq, const float* gamma,
 __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ y, uint4* __restrict__ z,
                                                         const float* __restrict__ scale,
                                                         const float* __restrict__ shift, long long nvec, int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = CV - 1 - (threadIdx.x % CV);  // mirrored traversal (see below)
   float a[8], c[8];
   {
@@ -363,7 +382,7 @@ cudaError_t bn_apply(const void* y, void* z, const float* scale, const float* sh
   const int CV = C / 8;
   if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
   const int threads = (256 / CV) * CV;  // a multiple of CV: the channel column of a thread is then constant
-  bn_apply_kernel<<<grid_for(nvec, threads * 4, 8), threads, 0, st>>>(static_cast<const uint4*>(y),
+  launch_k(bn_apply_kernel, dim3(grid_for(nvec, threads * 4, 8)), dim3(threads), 0, st, static_cast<const uint4*>(y),
                                                                       static_cast<uint4*>(z), scale, shift, nvec, CV);
   return cudaGetLastError();
 }
@@ -375,6 +394,8 @@ __global__ void bn_apply_pool_kernel(const uint4* __restrict__ y, uint4* __restr
                                      uint4* __restrict__ pooled, uint2* __restrict__ idx,
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      int N, int H, int W, int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(N) * Ho * Wo * CV;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -427,11 +448,11 @@ cudaError_t bn_apply_pool(const void* y, void* z, void* pooled, void* idx, const
                           const float* shift, int N, int H, int W, int C, cudaStream_t st) {
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
   if (scale != nullptr)
-    bn_apply_pool_kernel<true><<<grid_for(total, 256 * 2, 16), 256, 0, st>>>(
+    launch_k(bn_apply_pool_kernel<true>, dim3(grid_for(total, 256 * 2, 16)), dim3(256), 0, st, 
         static_cast<const uint4*>(y), static_cast<uint4*>(z), static_cast<uint4*>(pooled),
         static_cast<uint2*>(idx), scale, shift, N, H, W, C / 8);
   else
-    bn_apply_pool_kernel<false><<<grid_for(total, 256 * 2, 16), 256, 0, st>>>(
+    launch_k(bn_apply_pool_kernel<false>, dim3(grid_for(total, 256 * 2, 16)), dim3(256), 0, st, 
         static_cast<const uint4*>(y), nullptr, static_cast<uint4*>(pooled), static_cast<uint2*>(idx),
         nullptr, nullptr, N, H, W, C / 8);
   return cudaGetLastError();
@@ -441,6 +462,8 @@ cudaError_t bn_apply_pool(const void* y, void* z, void* pooled, void* idx, const
 __global__ void maxpool_bwd_add_kernel(const uint4* __restrict__ dpooled, const uint2* __restrict__ idx,
                                        const uint4* __restrict__ skip, uint4* __restrict__ din, int N,
                                        int H, int W, int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(N) * Ho * Wo * CV;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -480,7 +503,7 @@ __global__ void maxpool_bwd_add_kernel(const uint4* __restrict__ dpooled, const 
 cudaError_t maxpool_bwd_add(const void* dpooled, const void* idx, const void* skip, void* din, int N,
                             int H, int W, int C, cudaStream_t st) {
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * (C / 8);
-  maxpool_bwd_add_kernel<<<grid_for(total, 256 * 2, 16), 256, 0, st>>>(
+  launch_k(maxpool_bwd_add_kernel, dim3(grid_for(total, 256 * 2, 16)), dim3(256), 0, st, 
       static_cast<const uint4*>(dpooled), static_cast<const uint2*>(idx), static_cast<const uint4*>(skip),
       static_cast<uint4*>(din), N, H, W, C / 8);
   return cudaGetLastError();
@@ -521,6 +544,8 @@ __device__ __forceinline__ void channel_reduce(long long P, int CV, double* out0
 
 __global__ void bn_stats_kernel(const uint4* __restrict__ y, double* __restrict__ sum,
                                 double* __restrict__ sq, long long P, int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
   channel_reduce<2>(P, CV, sum, sq, [&](long long p, int cv, float* acc) {
     float f[8];
     unpack8(ldg_stream(y + p * CV + cv), f);
@@ -536,7 +561,7 @@ cudaError_t bn_stats(const void* y, double* sum, double* sq, long long P, int C,
   if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
   const int rows = 256 / CV;
   const size_t smem = static_cast<size_t>(rows) * CV * 16 * sizeof(float);
-  bn_stats_kernel<<<grid_for(P, rows * 8, 8), 256, smem, st>>>(static_cast<const uint4*>(y), sum, sq, P, CV);
+  launch_k(bn_stats_kernel, dim3(grid_for(P, rows * 8, 8)), dim3(256), smem, st, static_cast<const uint4*>(y), sum, sq, P, CV);
   return cudaGetLastError();
 }
 
@@ -544,6 +569,8 @@ cudaError_t bn_stats(const void* y, double* sum, double* sq, long long P, int C,
 __global__ void __launch_bounds__(256, 4)
     bn_bwd_reduce_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ y, double* __restrict__ s1,
                          double* __restrict__ s2, long long P, int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];
   const int rows = blockDim.x / CV;
   const int cv = threadIdx.x % CV;
@@ -597,7 +624,7 @@ cudaError_t bn_bwd_reduce(const void* dz, const void* y, double* s1, double* s2,
   if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
   const int rows = 256 / CV;
   const size_t smem = static_cast<size_t>(rows) * CV * 16 * sizeof(float);
-  bn_bwd_reduce_kernel<<<grid_for(P, rows * 8, 4), 256, smem, st>>>(
+  launch_k(bn_bwd_reduce_kernel, dim3(grid_for(P, rows * 8, 4)), dim3(256), smem, st, 
       static_cast<const uint4*>(dz), static_cast<const uint4*>(y), s1, s2, P, CV);
   return cudaGetLastError();
 }
@@ -609,6 +636,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ s1, const doub
                                        float* __restrict__ dbeta, float* __restrict__ kA,
                                        float* __restrict__ kB, float* __restrict__ kC, int C, double count,
                                        int training, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mu = mean[c], is = invstd[c], g = gamma[c];
@@ -634,7 +663,7 @@ cudaError_t bn_bwd_finalize(const double* s1, const double* s2, const float* gam
                             const float* invstd, float* dgamma, float* dbeta, float* kA, float* kB,
                             float* kC, int C, double count, int training, int accumulate,
                             cudaStream_t st) {
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(s1, s2, gamma, mean, invstd, dgamma, dbeta, kA,
+  launch_k(bn_bwd_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, st, s1, s2, gamma, mean, invstd, dgamma, dbeta, kA,
                                                           kB, kC, C, count, training, accumulate);
   return cudaGetLastError();
 }
@@ -644,6 +673,8 @@ __global__ void __launch_bounds__(256, 4)
     bn_relu_bwd_apply_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ y, uint4* __restrict__ dpre,
                              const float* __restrict__ kA, const float* __restrict__ kB,
                              const float* __restrict__ kC, double* __restrict__ dbias, long long P, int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];
   const int rows = blockDim.x / CV;
   const int cv = threadIdx.x % CV;
@@ -710,7 +741,7 @@ cudaError_t bn_relu_bwd_apply(const void* dz, const void* y, void* dpre, const f
   if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
   const int rows = 256 / CV;
   const size_t smem = static_cast<size_t>(rows) * CV * 8 * sizeof(float);
-  bn_relu_bwd_apply_kernel<<<grid_for(P, rows * 8, 4), 256, smem, st>>>(
+  launch_k(bn_relu_bwd_apply_kernel, dim3(grid_for(P, rows * 8, 4)), dim3(256), smem, st, 
       static_cast<const uint4*>(dz), static_cast<const uint4*>(y), static_cast<uint4*>(dpre), kA, kB, kC,
       dbias, P, CV);
   return cudaGetLastError();
@@ -719,6 +750,8 @@ cudaError_t bn_relu_bwd_apply(const void* dz, const void* y, void* dpre, const f
 // per-channel sum of a bf16 NHWC tensor (bias gradient of ConvTranspose2d / conv1x1)
 __global__ void channel_sum_kernel(const uint4* __restrict__ g, double* __restrict__ out, long long P,
                                    int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
   channel_reduce<1>(P, CV, out, out, [&](long long p, int cv, float* acc) {
     float f[8];
     unpack8(ldg_stream(g + p * CV + cv), f);
@@ -731,13 +764,15 @@ cudaError_t channel_sum(const void* g, double* out, long long P, int C, cudaStre
   if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
   const int rows = 256 / CV;
   const size_t smem = static_cast<size_t>(rows) * CV * 8 * sizeof(float);
-  channel_sum_kernel<<<grid_for(P, rows * 8, 8), 256, smem, st>>>(static_cast<const uint4*>(g), out, P, CV);
+  launch_k(channel_sum_kernel, dim3(grid_for(P, rows * 8, 8)), dim3(256), smem, st, static_cast<const uint4*>(g), out, P, CV);
   return cudaGetLastError();
 }
 
 // dst[i] = (accumulate ? dst[i] : 0) + alpha*src[i]   (fp64 accumulators -> fp32 .grad)
 __global__ void f64_to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int n, int ld_group,
                                   int groups, float alpha, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double s = 0.0;
@@ -747,7 +782,7 @@ __global__ void f64_to_f32_kernel(const double* __restrict__ src, float* __restr
 }
 cudaError_t f64_to_f32(const double* src, float* dst, int n, int ld_group, int groups, float alpha,
                        int accumulate, cudaStream_t st) {
-  f64_to_f32_kernel<<<(n + 127) / 128, 128, 0, st>>>(src, dst, n, ld_group, groups, alpha, accumulate);
+  launch_k(f64_to_f32_kernel, dim3((n + 127) / 128), dim3(128), 0, st, src, dst, n, ld_group, groups, alpha, accumulate);
   return cudaGetLastError();
 }
 
@@ -762,6 +797,8 @@ __global__ void __launch_bounds__(kLossPix)
                       const long long* __restrict__ labels, long long P, int C, int Cold, float T,
                       float lambda, float gscale, __nv_bfloat16* __restrict__ dlogits, int ldd,
                       double* __restrict__ loss_acc, int* __restrict__ err_flag) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];  // [256*C] new logits, [256*Cold] old logits
   float* sz = sm;
   float* so = sm + kLossPix * C;
@@ -864,7 +901,7 @@ cudaError_t ce_kd_loss(const float* logits, const float* old_logits, const long 
     cudaFuncSetAttribute(ce_kd_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr = true;
   }
-  ce_kd_loss_kernel<<<grid_for(P, kLossPix, 4), kLossPix, smem, st>>>(
+  launch_k(ce_kd_loss_kernel, dim3(grid_for(P, kLossPix, 4)), dim3(kLossPix), smem, st, 
       logits, old_logits, labels, P, C, Cold, T, lambda, gscale, static_cast<__nv_bfloat16*>(dlogits), ldd,
       loss_acc, err_flag);
   return cudaGetLastError();
@@ -888,6 +925,8 @@ __device__ __forceinline__ void hist_flush(unsigned int* sh, int nbins, int copi
 __global__ void __launch_bounds__(kHistThreads)
     confusion_kernel(const long long* __restrict__ target, const long long* __restrict__ pred,
                      long long n, int nc, unsigned long long* __restrict__ conf, int* __restrict__ err_flag) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ unsigned int sh[];  // [copies][nc*nc]
   const int nbins = nc * nc;
   const int copies = kHistThreads / 32;
@@ -926,7 +965,7 @@ cudaError_t confusion_matrix(const long long* target, const long long* pred, lon
   const size_t smem = static_cast<size_t>(kHistThreads / 32) * nc * nc * sizeof(unsigned int);
   if (smem > 48 * 1024) return cudaErrorInvalidValue;
   // each thread must see < 2^32 items per bin copy: guaranteed for n < 2^32 per block pass
-  confusion_kernel<<<grid_for(n / 2 + 1, kHistThreads * 8, 4), kHistThreads, smem, st>>>(
+  launch_k(confusion_kernel, dim3(grid_for(n / 2 + 1, kHistThreads * 8, 4)), dim3(kHistThreads), smem, st, 
       target, pred, n, nc, reinterpret_cast<unsigned long long*>(conf), err_flag);
   return cudaGetLastError();
 }
@@ -937,6 +976,8 @@ __global__ void __launch_bounds__(kHistThreads)
     argmax_confusion_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                             long long P, int C, int nc, long long* __restrict__ pred_out,
                             unsigned long long* __restrict__ conf, unsigned long long* __restrict__ correct) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ unsigned int sh[];  // [copies][nc*nc] then [256*C] floats
   const int nbins = nc * nc;
   const int copies = kHistThreads / 32;
@@ -982,7 +1023,7 @@ cudaError_t argmax_confusion(const float* logits, const long long* labels, long 
     cudaFuncSetAttribute(argmax_confusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr = true;
   }
-  argmax_confusion_kernel<<<grid_for(P, kHistThreads * 4, 4), kHistThreads, smem, st>>>(
+  launch_k(argmax_confusion_kernel, dim3(grid_for(P, kHistThreads * 4, 4)), dim3(kHistThreads), smem, st, 
       logits, labels, P, C, nc, pred_out, reinterpret_cast<unsigned long long*>(conf),
       reinterpret_cast<unsigned long long*>(correct));
   return cudaGetLastError();
@@ -994,6 +1035,8 @@ cudaError_t argmax_confusion(const float* logits, const long long* labels, long 
 __global__ void adam_kernel(const AdamTensor* __restrict__ tensors, const int2* __restrict__ blocks,
                             int chunk, float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
                             float gscale, const float* __restrict__ hyper) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (hyper != nullptr) {  // {lr, bc1, bc2_sqrt, gscale} in device memory (CUDA-graph replay)
     lr = hyper[0];
     bc1 = hyper[1];
@@ -1048,7 +1091,7 @@ cudaError_t adam_multi_tensor(const AdamTensor* tensors, const void* blocks, int
                               float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
                               float gscale, const float* hyper, cudaStream_t st) {
   if (nblocks <= 0) return cudaSuccess;
-  adam_kernel<<<nblocks, 256, 0, st>>>(tensors, static_cast<const int2*>(blocks), chunk, lr, b1, b2, eps,
+  launch_k(adam_kernel, dim3(nblocks), dim3(256), 0, st, tensors, static_cast<const int2*>(blocks), chunk, lr, b1, b2, eps,
                                        bc1, bc2_sqrt, gscale, hyper);
   return cudaGetLastError();
 }
@@ -1100,6 +1143,8 @@ __global__ void __launch_bounds__(256)
                           const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
                           float* __restrict__ mean_out, float* __restrict__ invstd_out, long long nvec, int CV,
                           double count, float eps, float momentum, int training) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = CV - 1 - (threadIdx.x % CV);
   BnCoef k;
   // in training mode the running statistics are read-modify-written by block 0 only; other blocks never read them
@@ -1132,7 +1177,7 @@ cudaError_t bn_apply_fused(const void* y, void* z, const double* sum, const doub
   if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
   const long long nvec = P * CV;
   const int threads = (256 / CV) * CV;
-  bn_apply_fused_kernel<<<grid_for(nvec, threads * 4, 8), threads, 0, st>>>(
+  launch_k(bn_apply_fused_kernel, dim3(grid_for(nvec, threads * 4, 8)), dim3(threads), 0, st, 
       static_cast<const uint4*>(y), static_cast<uint4*>(z), sum, sq, gamma, beta, rmean, rvar, mean_out, invstd_out,
       nvec, CV, count, eps, momentum, training);
   return cudaGetLastError();
@@ -1145,6 +1190,8 @@ __global__ void __launch_bounds__(256)
                                float* __restrict__ rmean, float* __restrict__ rvar, float* __restrict__ mean_out,
                                float* __restrict__ invstd_out, int N, int H, int W, int CV, double count, float eps,
                                float momentum, int training) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2;
   const long long total = static_cast<long long>(N) * Ho * Wo * CV;
   const int cv = threadIdx.x % CV;  // blockDim is a multiple of CV
@@ -1197,7 +1244,7 @@ cudaError_t bn_apply_pool_fused(const void* y, void* z, void* pooled, void* idx,
   if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
   const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * CV;
   const int threads = (256 / CV) * CV;
-  bn_apply_pool_fused_kernel<<<grid_for(total, threads * 2, 8), threads, 0, st>>>(
+  launch_k(bn_apply_pool_fused_kernel, dim3(grid_for(total, threads * 2, 8)), dim3(threads), 0, st, 
       static_cast<const uint4*>(y), static_cast<uint4*>(z), static_cast<uint4*>(pooled), static_cast<uint2*>(idx),
       sum, sq, gamma, beta, rmean, rvar, mean_out, invstd_out, N, H, W, CV, count, eps, momentum, training);
   return cudaGetLastError();
@@ -1212,6 +1259,8 @@ __global__ void __launch_bounds__(256, 4)
                                    const float* __restrict__ invstd, float* __restrict__ dgamma,
                                    float* __restrict__ dbeta, double* __restrict__ dbias, long long P, int CV,
                                    double count, int training) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];
   const int rows = blockDim.x / CV;
   const int cv = threadIdx.x % CV;
@@ -1283,7 +1332,7 @@ cudaError_t bn_relu_bwd_apply_fused(const void* dz, const void* y, void* dpre, c
   if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
   const int rows = 256 / CV;
   const size_t smem = static_cast<size_t>(rows) * CV * 8 * sizeof(float);
-  bn_relu_bwd_apply_fused_kernel<<<grid_for(P, rows * 8, 4), 256, smem, st>>>(
+  launch_k(bn_relu_bwd_apply_fused_kernel, dim3(grid_for(P, rows * 8, 4)), dim3(256), smem, st, 
       static_cast<const uint4*>(dz), static_cast<const uint4*>(y), static_cast<uint4*>(dpre), s1, s2, gamma, mean,
       invstd, dgamma, dbeta, dbias, P, CV, count, training);
   return cudaGetLastError();
@@ -1301,6 +1350,8 @@ __device__ __forceinline__ int find_job(const long long* __restrict__ jobs, int 
 
 // row: {src, outAB, outBA, A, B, T, ldA, ldB, ldB2, ldA2, rev, tile0, tiles_b, -, -, -}
 __global__ void __launch_bounds__(256) pack_w_multi_kernel(const long long* __restrict__ jobs, int njobs) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float tile[];  // [32][32*T + 1]
   const int j = find_job(jobs, njobs, blockIdx.x, 11);
   const long long* J = jobs + j * 16;
@@ -1341,12 +1392,14 @@ __global__ void __launch_bounds__(256) pack_w_multi_kernel(const long long* __re
 cudaError_t pack_w_multi(const void* jobs, int njobs, int total_tiles, int max_T, cudaStream_t st) {
   if (total_tiles <= 0) return cudaSuccess;
   const size_t smem = static_cast<size_t>(32) * (32 * max_T + 1) * sizeof(float);
-  pack_w_multi_kernel<<<total_tiles, 256, smem, st>>>(static_cast<const long long*>(jobs), njobs);
+  launch_k(pack_w_multi_kernel, dim3(total_tiles), dim3(256), smem, st, static_cast<const long long*>(jobs), njobs);
   return cudaGetLastError();
 }
 
 // row: {D, grad, A, B, T, ldA, ldB, alpha (double bits), accumulate, tile0, tiles_b, ...}
 __global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const long long* __restrict__ jobs, int njobs) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float tile[];
   const int j = find_job(jobs, njobs, blockIdx.x, 9);
   const long long* J = jobs + j * 16;
@@ -1391,13 +1444,15 @@ __global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const long long
 cudaError_t unpack_wgrad_multi(const void* jobs, int njobs, int total_tiles, int max_T, cudaStream_t st) {
   if (total_tiles <= 0) return cudaSuccess;
   const size_t smem = static_cast<size_t>(32) * (32 * max_T + 1) * sizeof(float);
-  unpack_wgrad_multi_kernel<<<total_tiles, 256, smem, st>>>(static_cast<const long long*>(jobs), njobs);
+  launch_k(unpack_wgrad_multi_kernel, dim3(total_tiles), dim3(256), smem, st, static_cast<const long long*>(jobs), njobs);
   return cudaGetLastError();
 }
 
 // split-K partial buffers -> their sum, in place in split 0 (fixed summation order: deterministic).
 // row: {base, n_vec4, nsplit, stride_vec4, block0}; one thread per float4, 8 independent loads in flight.
 __global__ void __launch_bounds__(256) reduce_partials_multi_kernel(const long long* __restrict__ jobs, int njobs) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int j = find_job(jobs, njobs, blockIdx.x, 4);
   const long long* J = jobs + j * 16;
   float4* base = reinterpret_cast<float4*>(J[0]);
@@ -1425,12 +1480,14 @@ __global__ void __launch_bounds__(256) reduce_partials_multi_kernel(const long l
 }
 cudaError_t reduce_partials_multi(const void* jobs, int njobs, int total_blocks, cudaStream_t st) {
   if (total_blocks <= 0) return cudaSuccess;
-  reduce_partials_multi_kernel<<<total_blocks, 256, 0, st>>>(static_cast<const long long*>(jobs), njobs);
+  launch_k(reduce_partials_multi_kernel, dim3(total_blocks), dim3(256), 0, st, static_cast<const long long*>(jobs), njobs);
   return cudaGetLastError();
 }
 
 // row: {src f64, dst f32, n, ld_group, groups, alpha (double bits), accumulate}; one block per job
 __global__ void f64_to_f32_multi_kernel(const long long* __restrict__ jobs) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long* J = jobs + blockIdx.x * 16;
   const double* __restrict__ src = reinterpret_cast<const double*>(J[0]);
   float* __restrict__ dst = reinterpret_cast<float*>(J[1]);
@@ -1446,7 +1503,7 @@ __global__ void f64_to_f32_multi_kernel(const long long* __restrict__ jobs) {
 }
 cudaError_t f64_to_f32_multi(const void* jobs, int njobs, cudaStream_t st) {
   if (njobs <= 0) return cudaSuccess;
-  f64_to_f32_multi_kernel<<<njobs, 256, 0, st>>>(static_cast<const long long*>(jobs));
+  launch_k(f64_to_f32_multi_kernel, dim3(njobs), dim3(256), 0, st, static_cast<const long long*>(jobs));
   return cudaGetLastError();
 }
 

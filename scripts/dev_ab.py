@@ -36,14 +36,31 @@ def time_cfg(flags, tune, steps=40):
 
 if __name__ == "__main__":
     base = dict(use_side_stream=True, fuse_bn=False, side_pack=True)
-    variants = [("default", {}, {}), ("fuse_bn", dict(fuse_bn=True), {}), ("no side_pack", dict(side_pack=False), {}),
-                ("no side stream", dict(use_side_stream=False, side_pack=False), {}),
-                ("default (repeat)", {}, {}), ("fprop_bn=64", {}, {"fprop_bn": 64}), ("conv3 generic only", {}, {"conv3_v2": 0}),
-                ("conv3 halo 1-CTA everywhere", {}, {"conv3_v2": 2, "conv3_pair": 0}), ("conv3 hybrid (round-1 mid)", {}, {"conv3_v2": 1, "conv3_pair": 1}), ("default (again)", {}, {"fprop_bn": 0, "conv3_v2": 4, "wgrad_v2": 1})]
+    nos = dict(use_side_stream=False, side_pack=False)
+    variants = [("default", {}, {}), ("pdl off", {}, {"pdl": 0}),
+                ("pdl, tensor trigger at start", {}, {"pdl": 1, "pdl_tensor_trigger": 0}),
+                ("pdl, trigger after last load", {}, {"pdl_tensor_trigger": 1}),
+                ("pdl, trigger at exit", {}, {"pdl_tensor_trigger": 2}),
+                ("pdl off", {}, {"pdl": 0}),
+                ("pdl, tensor trigger at start", {}, {"pdl": 1, "pdl_tensor_trigger": 0}),
+                ("pdl, trigger after last load", {}, {"pdl_tensor_trigger": 1}),
+                ("pdl, trigger at exit", {}, {"pdl_tensor_trigger": 2}),
+                ("1 stream, pdl off", nos, {"pdl": 0}),
+                ("1 stream, trigger at start", nos, {"pdl": 1, "pdl_tensor_trigger": 0}),
+                ("1 stream, trigger after last load", nos, {"pdl_tensor_trigger": 1}),
+                ("1 stream, trigger at exit", nos, {"pdl_tensor_trigger": 2}),
+                ("default", {}, {"pdl_tensor_trigger": 1})]
+    if "--all" in sys.argv:
+        sys.argv.remove("--all")
+        variants += [("fuse_bn", dict(fuse_bn=True), {"pdl": 1}), ("no side_pack", dict(side_pack=False), {}),
+                     ("fprop_bn=64", {}, {"fprop_bn": 64}), ("conv3 generic only", {}, {"fprop_bn": 0, "conv3_v2": 0}),
+                     ("conv3 halo 1-CTA everywhere", {}, {"conv3_v2": 2, "conv3_pair": 0}),
+                     ("wgrad 1-CTA halo", {}, {"conv3_v2": 4, "conv3_pair": 1, "wgrad_v2": 1}),
+                     ("default (again)", {}, {"wgrad_v2": 2})]
     for extra in sys.argv[1:]:
         k, v = extra.split("=")
         variants.append((extra, {}, {k: int(v)}))
     for name, fl, tune in variants:
         f = dict(base)
         f.update(fl)
-        print(f"{name:24s} {time_cfg(f, tune):8.3f} ms/step", flush=True)
+        print(f"{name:36s} {time_cfg(f, tune):8.3f} ms/step", flush=True)
