@@ -527,6 +527,30 @@ int clk_conv3x3_wgrad(const void* dy, int Cout, const void* x0, int C0, const vo
   return cuda_status(launch_wgrad(BN, u, t0, t1, p, S(st)), "conv3x3_wgrad");
 }
 
+// ------------------------------------------------------------------ fused head + loss + head backward
+int clk_head_loss_bwd(const void* z, const void* wf, const void* wd, const float* bias, const int64_t* labels,
+                      const float* old_logits, long long P, int Cin, int C, int Cold, float T, float lambda,
+                      float gscale, void* dz, float* dw, double* dbias, double* loss_acc, int* err_flag,
+                      clk_stream_t st) {
+  if (!z || !wf || !wd || !labels || !dz || !dw || !dbias || !loss_acc || P <= 0)
+    return fail(CLK_E_BADARG, "head_loss_bwd: bad args");
+  if (Cin != 64 || C < 1 || C > 32 || Cold < 0 || Cold > C || (old_logits != nullptr) != (Cold > 0))
+    return fail(CLK_E_UNSUPPORTED_SHAPE, "head_loss_bwd: needs Cin == 64, 1 <= C <= 32, Cold <= C (Cin=%d C=%d Cold=%d)",
+                Cin, C, Cold);
+  if (P > 2000000000LL) return fail(CLK_E_UNSUPPORTED_SHAPE, "head_loss_bwd: P too large");
+  if (old_logits != nullptr && !(T > 0.f)) return fail(CLK_E_BADARG, "head_loss_bwd: T must be positive");
+  HeadLossParams q;
+  memset(&q, 0, sizeof(q));
+  q.P = P; q.C = C; q.Cold = Cold; q.T = old_logits ? T : 1.f; q.lambda = lambda; q.gscale = gscale;
+  q.bias = bias; q.labels = reinterpret_cast<const long long*>(labels); q.old_logits = old_logits;
+  q.dz = dz; q.dw = dw; q.dbias = dbias; q.loss_acc = loss_acc; q.err_flag = err_flag;
+  CUtensorMap mz, mf, md;
+  CHECK_RC(map_linear(&mz, z, P, 64, 128));
+  CHECK_RC(map_weights(&mf, wf, 1, 32, 64, 32));
+  CHECK_RC(map_weights(&md, wd, 1, 64, 64, 64));
+  return cuda_status(launch_head_loss(mz, mf, md, q, g_num_sms_api, S(st)), "head_loss_bwd");
+}
+
 // ------------------------------------------------------------------ igemm: plain GEMMs
 static int gemm_fprop_impl(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
                           int out_is_f32, int relu, double* stat_sum, double* stat_sq, const float* bn_scale,

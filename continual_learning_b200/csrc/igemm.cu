@@ -8,6 +8,7 @@
 // Replaces (reference): nn.Conv2d 3x3 / 1x1, nn.ConvTranspose2d 2x2 s2 forward and backward as
 // dispatched by models/unet.py:13,16,28,31,34,50,53,66,69,72 and autograd (trainer.py:175).
 #include "igemm.cuh"
+#include <math_constants.h>
 
 #include "clk_ptx.cuh"
 
@@ -1551,6 +1552,289 @@ cudaError_t launch_wgrad(int BN, const CUtensorMap& u, const CUtensorMap& t0, co
     case 128: return launch_wgrad_t<128>(u, t0, t1, p, st);
     default: return cudaErrorInvalidValue;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// HEAD + LOSS + HEAD BACKWARD in one kernel (models/unet.py:72, trainer.py:113,174-175 for the head):
+//   logits = z Wf^T + b        tcgen05, fp32 logits stay in tensor memory (never written to HBM)
+//   CE (+ temperature-KL)      one thread per pixel on its TMEM row; dlogits -> bf16 -> shared memory (swizzled)
+//   dz = dlogits Wd            tcgen05, A = the dlogits tile just written           -> bf16 [P][64]
+//   dW += dlogits^T z          tcgen05, the SAME two tiles read MN-major, accumulated in TMEM over the CTA's tiles
+//   db += colsum(dlogits)      warp shuffles
+// HBM traffic: z read once, dz written once, labels (+ old logits) read once: 276 B/pixel instead of ~1.2 KB/pixel
+// for the five separate launches.  128 threads per CTA (thread = pixel = TMEM lane), three CTAs per SM hide the
+// per-tile dependency chain (MMA -> CE -> MMA -> store); thread 0 issues TMA and MMAs.
+constexpr int kHlThreads = 128;
+constexpr int kHlTile = 128 * 128;                 // [128 px][64 ch] bf16
+constexpr int kHlSmem = 3 * kHlTile + 32 * 128 + 64 * 128 + 8 * 8 + 16 + 1024;
+
+__global__ void __launch_bounds__(kHlThreads, 3)
+    head_loss_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapWf,
+                     const __grid_constant__ CUtensorMap mapWd, const __grid_constant__ HeadLossParams p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sD = smem;                       // dlogits tile [128 px][64 cls] bf16, SWIZZLE_128B rows
+  uint8_t* sZ = smem + kHlTile;             // two z stages (the first doubles as the ignored upper half of M in dW)
+  uint8_t* sWf = sZ + 2 * kHlTile;          // [32 cls][64 ch]
+  uint8_t* sWd = sWf + 32 * 128;            // [64 ch][64 cls]
+  uint64_t* z_full = reinterpret_cast<uint64_t*>(sWd + 64 * 128);
+  uint64_t* w_full = z_full + 2;
+  uint64_t* mma_bar = w_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long tiles = (p.P + 127) / 128;
+  if (tid == 0) {
+    mbar_init(&z_full[0], 1);
+    mbar_init(&z_full[1], 1);
+    mbar_init(w_full, 1);
+    mbar_init(mma_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&mapZ);
+    tma_prefetch_desc(&mapWf);
+    tma_prefetch_desc(&mapWd);
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  // the zero half of this thread's dlogits row (classes 32..63) is written once
+  {
+    uint4* row = reinterpret_cast<uint4*>(sD + tid * 128);
+#pragma unroll
+    for (int c = 4; c < 8; ++c) row[c ^ (tid & 7)] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (tid == 0) {
+    mbar_arrive_expect_tx(w_full, 32 * 128 + 64 * 128);
+    tma_load_3d(sWf, &mapWf, w_full, 0, 0, 0);
+    tma_load_3d(sWd, &mapWd, w_full, 0, 0, 0);
+    for (int s = 0; s < 2; ++s) {
+      const long long t = static_cast<long long>(blockIdx.x) + static_cast<long long>(s) * gridDim.x;
+      if (t < tiles) {
+        mbar_arrive_expect_tx(&z_full[s], kHlTile);
+        tma_load_5d(sZ + s * kHlTile, &mapZ, &z_full[s], 0, static_cast<int>(t * 128), 0, 0, 0);
+      }
+    }
+  }
+
+  constexpr uint32_t idesc_logits = umma_idesc_bf16(128, 32, 0, 0);
+  constexpr uint32_t idesc_dz = umma_idesc_bf16(128, 64, 0, 0);
+  constexpr uint32_t idesc_dw = umma_idesc_bf16(128, 64, 1, 1);
+  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const float invT = 1.f / p.T;
+  const bool kd_on = p.old_logits != nullptr;
+  float ce_local = 0.f, kd_local = 0.f, db_local = 0.f;
+  uint32_t ph = 0;  // phase of mma_bar
+  uint32_t it = 0;
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+    const uint32_t s = it & 1;
+    const uint32_t zaddr = smem_u32(sZ + s * kHlTile);
+    // ---- logits[128][32] = Z[128][64] Wf^T
+    if (tid == 0) {
+      if (it == 0) mbar_wait(w_full, 0);
+      mbar_wait(&z_full[s], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_base, umma_smem_desc(zaddr + k * 32, 16, 1024), umma_smem_desc(smem_u32(sWf) + k * 32, 16, 1024),
+                  idesc_logits, k != 0 ? 1u : 0u);
+      umma_commit(mma_bar);
+    }
+    mbar_wait(mma_bar, ph);
+    ph ^= 1;
+    tc_fence_after();
+    // ---- softmax cross-entropy (+ distillation) on this thread's pixel
+    const long long pix = t * 128 + tid;
+    const bool valid = pix < p.P;
+    float g[32];
+    {
+      uint32_t v[32];
+      tmem_ld32(lane_addr, v);
+      tmem_ld_wait();
+      float z[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) z[c] = __uint_as_float(v[c]) + (c < p.C ? p.bias[c] : 0.f);
+      const long long y = valid ? p.labels[pix] : 0;
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < p.C) mx = fmaxf(mx, z[c]);
+      float se = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < p.C) se += __expf(z[c] - mx);
+      const float lse = mx + __logf(se);
+      const float inv_se = 1.f / se;
+      const bool yok = y >= 0 && y < p.C;
+      if (valid && !yok && p.err_flag != nullptr) *p.err_flag = 1;
+      if (valid && yok) {
+        float zy = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) zy = (c == y) ? z[c] : zy;
+        ce_local += lse - zy;
+      }
+      float lq = 0.f, lo = 0.f;
+      float zo[32];
+      if (kd_on) {
+        const float* orow = p.old_logits + (valid ? pix : 0) * p.Cold;
+        float mq = -CUDART_INF_F, mo = -CUDART_INF_F;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          zo[c] = (c < p.Cold) ? orow[c] : 0.f;
+          if (c < p.Cold) {
+            mq = fmaxf(mq, z[c] * invT);
+            mo = fmaxf(mo, zo[c] * invT);
+          }
+        }
+        float sq = 0.f, so = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < p.Cold) {
+            sq += __expf(z[c] * invT - mq);
+            so += __expf(zo[c] * invT - mo);
+          }
+        lq = mq + __logf(sq);
+        lo = mo + __logf(so);
+      }
+      float kd = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        float d = 0.f;
+        if (valid && c < p.C) {
+          d = yok ? (__expf(z[c] - mx) * inv_se - (c == y ? 1.f : 0.f)) : 0.f;
+          if (kd_on && c < p.Cold) {
+            const float logq = z[c] * invT - lq;
+            const float logp0 = zo[c] * invT - lo;
+            const float p0 = __expf(logp0);
+            kd += p0 * (logp0 - logq);
+            d += p.lambda * p.T * (__expf(logq) - p0);
+          }
+          d *= p.gscale;
+        }
+        g[c] = d;
+      }
+      kd_local += kd;
+    }
+    // dlogits row -> bf16 -> shared memory in the SWIZZLE_128B pattern TMA would have produced
+    {
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(g[2 * j], g[2 * j + 1]);
+      uint4* row = reinterpret_cast<uint4*>(sD + tid * 128);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        row[c ^ (tid & 7)] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {  // the bias gradient sums what the tensor core will see (bf16-rounded)
+        g[2 * j] = bf16lo_to_f32(pk[j]);
+        g[2 * j + 1] = bf16hi_to_f32(pk[j]);
+      }
+      db_local += warp_colsum32(g, lane);
+    }
+    tc_fence_before();     // the logits were read out of TMEM before the next MMA overwrites them
+    fence_proxy_async();   // generic-proxy writes of the dlogits tile -> visible to the tensor core (async proxy)
+    __syncthreads();
+    // ---- dz[128][64] = D[128][32] Wd^T (columns 0..63 of TMEM) and dW[cls][ch] += D^T Z (columns 64..127)
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t daddr = smem_u32(sD);
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+        umma_bf16(tmem_base, umma_smem_desc(daddr + k * 32, 16, 1024), umma_smem_desc(smem_u32(sWd) + k * 32, 16, 1024),
+                  idesc_dz, k != 0 ? 1u : 0u);
+      // MN-major views: A = D^T (M = class; rows 64..127 of M read the first z stage and are never used),
+      // B = Z^T-free view of the same z tile (N = channel), K = the 128 pixels in 8 steps of 16 rows
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(tmem_base + 64, umma_smem_desc(daddr + k * 2048, kHlTile, 1024),
+                  umma_smem_desc(zaddr + k * 2048, kHlTile, 1024), idesc_dw, (it | k) != 0 ? 1u : 0u);
+      umma_commit(mma_bar);
+    }
+    mbar_wait(mma_bar, ph);
+    ph ^= 1;
+    tc_fence_after();
+    if (tid == 0) {  // z stage s is free again: request the tile after next
+      const long long tn = t + 2ll * gridDim.x;
+      if (tn < tiles) {
+        mbar_arrive_expect_tx(&z_full[s], kHlTile);
+        tma_load_5d(sZ + s * kHlTile, &mapZ, &z_full[s], 0, static_cast<int>(tn * 128), 0, 0, 0);
+      }
+    }
+    // ---- dz row -> bf16 -> global
+    {
+      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.dz) + (valid ? pix : 0) * 64;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(lane_addr + half * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+          uint4* o = reinterpret_cast<uint4*>(orow + half * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            o[j] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                              pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                              pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                              pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // every thread is done with TMEM columns 0..63 and with the dlogits tile
+  }
+
+  // ---- flush: weight gradient (TMEM lanes = classes), bias gradient, loss
+  if (it > 0) {
+    if (warp == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + 64 + half * 32, v);
+        tmem_ld_wait();
+        if (lane < p.C) {
+          float* o = p.dw + lane * 64 + half * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            red_add_v4(o + 4 * j, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                       __uint_as_float(v[4 * j + 3]));
+        }
+      }
+    }
+    if (lane < p.C) atomicAdd(&p.dbias[lane], static_cast<double>(db_local));
+    for (int o = 16; o > 0; o >>= 1) {
+      ce_local += __shfl_xor_sync(0xffffffffu, ce_local, o);
+      kd_local += __shfl_xor_sync(0xffffffffu, kd_local, o);
+    }
+    if (lane == 0) {
+      atomicAdd(p.loss_acc, static_cast<double>(ce_local));
+      if (kd_on) atomicAdd(p.loss_acc + 1, static_cast<double>(kd_local));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+cudaError_t launch_head_loss(const CUtensorMap& z, const CUtensorMap& wf, const CUtensorMap& wd, const HeadLossParams& p,
+                             int num_sms, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(head_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHlSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  long long grid = (p.P + 127) / 128;
+  if (grid > 3ll * num_sms) grid = 3ll * num_sms;
+  launch_k(head_loss_kernel, dim3(static_cast<unsigned>(grid)), dim3(kHlThreads), kHlSmem, st, z, wf, wd, p);
+  return cudaGetLastError();
 }
 
 }  // namespace clk

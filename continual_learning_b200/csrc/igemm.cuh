@@ -121,4 +121,22 @@ cudaError_t launch_conv3x2(int BN, const CUtensorMap& a0, const CUtensorMap& a1,
 cudaError_t launch_conv3(int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                          const Conv3Params& p, int num_sms, cudaStream_t st);
 
+// fused 1x1 head + softmax cross-entropy (+ distillation) + head backward, see head_loss_kernel
+struct HeadLossParams {
+  long long P;
+  int C, Cold;
+  float T, lambda, gscale;
+  const float* bias;
+  const long long* labels;
+  const float* old_logits;   // fp32 [P][Cold] or null
+  void* dz;                  // bf16 [P][64]
+  float* dw;                 // fp32 [>= C][64], accumulated
+  double* dbias;             // f64[>= C], accumulated
+  double* loss_acc;          // f64[2], accumulated
+  int* err_flag;
+};
+// z box {64, 128}; wf box {64, 32, 1}; wd box {64, 64, 1}
+cudaError_t launch_head_loss(const CUtensorMap& z, const CUtensorMap& wf, const CUtensorMap& wd, const HeadLossParams& p,
+                             int num_sms, cudaStream_t st);
+
 }  // namespace clk

@@ -290,9 +290,11 @@ class UNetEngine:
             pool=pool)
         return u.z
 
-    def forward(self, x, training=True, save_for_backward=True):
+    def forward(self, x, training=True, save_for_backward=True, head=True):
         """x: fp32 NCHW CUDA tensor. Returns fp32 logits [N, H, W, num_classes] (NHWC memory).
-        save_for_backward=False (with training=False) selects the fused inference kernels."""
+        save_for_backward=False (with training=False) selects the fused inference kernels.
+        head=False stops before the 1x1 head and returns its bf16 input [N, H, W, 64] (TrainStep fuses the head with
+        the loss and the head's backward, see `head_loss_backward`)."""
         self.save_for_backward = save_for_backward
         if not x.is_cuda:
             raise RuntimeError("continual_learning_b200.UNet runs on CUDA (sm_100a) only: there is no CPU fallback")
@@ -330,12 +332,27 @@ class UNetEngine:
             up = ops.convT_fprop(z, self.twf[j], self.convT[j][0].bias.detach())
         z = self._unit_fwd(U[16], U[1].z, up, training)
         z = self._unit_fwd(U[17], z, None, training)
-        self.logits = ops.gemm_fprop(z, self.hwf, self.head.bias.detach(), self.m.num_classes, out_f32=True)
         if training:
             bufs = [u.bn.num_batches_tracked for u in U if u.bn.num_batches_tracked is not None]
             if bufs:
                 torch._foreach_add_(bufs, 1)
+        if not head:
+            self.logits = None
+            return z
+        self.logits = ops.gemm_fprop(z, self.hwf, self.head.bias.detach(), self.m.num_classes, out_f32=True)
         return self.logits
+
+    def head_loss_backward(self, labels, loss_acc, old_logits=None, T=2.0, lam=1.0, err_flag=None, after_decoder=None):
+        """after forward(head=False): 1x1 head + CrossEntropy (+ distillation) + the head's backward in one launch,
+        then the rest of the backward pass.  Adds {sum CE, sum KL} to loss_acc (f64[2]); returns the gradient views."""
+        U = self.units
+        z = U[17].z
+        self._begin_backward()
+        n, h, w = z.shape[0], z.shape[1], z.shape[2]
+        _, dz, _, _ = ops.head_loss_bwd(z, self.hwf, self.hwd, self.head.bias.detach(), labels, self.m.num_classes,
+                                        old_logits=old_logits, T=T, lam=lam, gscale=1.0 / (n * h * w), dw=self.hgp,
+                                        dbias=self.hdbias, loss_acc=loss_acc, err_flag=err_flag)
+        return self.backward(None, after_decoder=after_decoder, dz_head=dz)
 
     # ------------------------------------------------------------------ backward
     def _unit_bwd(self, u, dz, need_dx=True):
@@ -413,23 +430,29 @@ class UNetEngine:
         self._forked = False
         self._pending = []
 
-    def backward(self, dlogits, after_decoder=None):
-        """dlogits: bf16 [N, H, W, 64] (columns >= num_classes zero). Fills the flat gradient buffer and
-        returns the per-parameter gradient views (PyTorch layouts) in `module.parameters()` order.
-        `after_decoder()` is called once the head + decoder gradients are final (85 % of the bytes), so a
-        data-parallel caller can start reducing them while the encoder backward still runs."""
-        U = self.units
-        nc = self.m.num_classes
+    def _begin_backward(self):
         if not self.save_for_backward:
             raise RuntimeError("backward() after an inference forward (save_for_backward=False): the fused "
                                "conv+BatchNorm kernels keep no pre-BN activations")
         self.acc_b.zero_()
         self.Gp.zero_()
-        # 1x1 head (models/unet.py:72)
-        with self._fork(dlogits):
-            ops.gemm_wgrad(dlogits, U[17].z, out=self.hgp)
-            ops.channel_sum(dlogits, self.hdbias)
-        dz = ops.gemm_fprop(dlogits, self.hwd, None, self.m.conv_dim)
+
+    def backward(self, dlogits, after_decoder=None, dz_head=None):
+        """dlogits: bf16 [N, H, W, 64] (columns >= num_classes zero). Fills the flat gradient buffer and
+        returns the per-parameter gradient views (PyTorch layouts) in `module.parameters()` order.
+        `after_decoder()` is called once the head + decoder gradients are final (85 % of the bytes), so a
+        data-parallel caller can start reducing them while the encoder backward still runs.
+        dz_head: the head's input gradient when `head_loss_backward` already did the head (dlogits is then None)."""
+        U = self.units
+        if dz_head is None:
+            self._begin_backward()
+            # 1x1 head (models/unet.py:72)
+            with self._fork(dlogits):
+                ops.gemm_wgrad(dlogits, U[17].z, out=self.hgp)
+                ops.channel_sum(dlogits, self.hdbias)
+            dz = ops.gemm_fprop(dlogits, self.hwd, None, self.m.conv_dim)
+        else:
+            dz = dz_head
         dz, _ = self._unit_bwd(U[17], dz)
         skip_grads = []
         dskip, dup = self._unit_bwd(U[16], dz)

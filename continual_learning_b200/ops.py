@@ -332,6 +332,25 @@ def ce_kd_loss(logits, labels, old_logits=None, T=2.0, lam=1.0, gscale=None, dlo
     return loss_acc, dlogits
 
 
+def head_loss_bwd(z, wf, wd, bias, labels, num_classes, old_logits=None, T=2.0, lam=1.0, gscale=None, dz=None, dw=None,
+                  dbias=None, loss_acc=None, err_flag=None):
+    """1x1 head + CE (+ distillation) + head backward in one launch (the logits never leave tensor memory).
+    z bf16 [..., 64]; returns (loss_acc f64[2], dz bf16 like z, dw f32 [64, 64] (rows = class), dbias f64[64])."""
+    _dev(z)
+    cin = z.shape[-1]
+    p = z.numel() // cin
+    cold = 0 if old_logits is None else old_logits.shape[-1]
+    dev = z.device
+    dz = torch.empty_like(z) if dz is None else dz
+    dw = torch.zeros((64, cin), device=dev, dtype=torch.float32) if dw is None else dw
+    dbias = torch.zeros(64, device=dev, dtype=torch.float64) if dbias is None else dbias
+    loss_acc = torch.zeros(2, device=dev, dtype=torch.float64) if loss_acc is None else loss_acc
+    gscale = 1.0 / p if gscale is None else gscale
+    _lib.call("clk_head_loss_bwd", z, wf, wd, bias, labels, old_logits, p, cin, num_classes, cold, float(T), float(lam),
+              float(gscale), dz, dw, dbias, loss_acc, err_flag)
+    return loss_acc, dz, dw, dbias
+
+
 def confusion_matrix(target, pred, nc, conf=None, err_flag=None):
     if conf is None:
         conf = torch.zeros(nc * nc, device=target.device, dtype=torch.int64)

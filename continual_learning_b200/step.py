@@ -22,6 +22,8 @@ class TrainStep:
         # with a communicator the step runs eagerly: capturing the NCCL all-reduces into the graph hung on
         # B200 x2 (torch 2.11 / NCCL 2.28.9), and the eager step is GPU-bound anyway (7.28 vs 7.0 ms at N=2 vs 1)
         self.use_graph = use_graph and comm is None
+        # head GEMM + loss + head backward as one kernel (needs the reference geometry: 64 channels, <= 32 classes)
+        self.fused_head = model.conv_dim == 64 and model.num_classes <= 32
         self.comm = comm  # parallel.GradAllReduce or None
         self.graph = None
         self.shape = None
@@ -38,14 +40,24 @@ class TrainStep:
             oeng = self.old.engine
             old_logits = oeng.forward(x, training=False, save_for_backward=False)
             oeng.release()
-        logits = eng.forward(x, training=self.model.training)
-        self.loss_acc.zero_()
-        ops.ce_kd_loss(logits, y, old_logits, T=self.T, lam=self.lam, dlogits=self.dlogits, loss_acc=self.loss_acc,
-                       err_flag=self.err_flag)
         hook = None
         if self.comm is not None:
             hook = lambda: self.comm.start_decoder(eng.G)
-        views = eng.backward(self.dlogits, after_decoder=hook)
+        if self.fused_head:
+            # the logits never reach HBM: head GEMM, loss and the head's backward are one kernel
+            eng.forward(x, training=self.model.training, head=False)
+            self.loss_acc.zero_()
+            views = eng.head_loss_backward(y, self.loss_acc, old_logits=old_logits, T=self.T, lam=self.lam,
+                                           err_flag=self.err_flag, after_decoder=hook)
+        else:
+            logits = eng.forward(x, training=self.model.training)
+            self.loss_acc.zero_()
+            if self.dlogits is None:
+                n, _, h, w = x.shape
+                self.dlogits = torch.zeros((n, h, w, 64), device=x.device, dtype=torch.bfloat16)
+            ops.ce_kd_loss(logits, y, old_logits, T=self.T, lam=self.lam, dlogits=self.dlogits, loss_acc=self.loss_acc,
+                           err_flag=self.err_flag)
+            views = eng.backward(self.dlogits, after_decoder=hook)
         eng.release()
         for p, v in zip(eng.params, views):
             if p.grad is not v:  # first step, or the module was moved (.cpu()/.cuda() in save_network)
@@ -62,7 +74,7 @@ class TrainStep:
         self.shape = (tuple(x.shape), tuple(y.shape))
         self.x_static = torch.empty_like(x)
         self.y_static = torch.empty_like(y)
-        self.dlogits = torch.zeros((n, h, w, 64), device=dev, dtype=torch.bfloat16)
+        self.dlogits = None  # only the unfused path materialises the logits gradient
         self.loss_acc = torch.zeros(2, device=dev, dtype=torch.float64)
         self.err_flag = torch.zeros(1, device=dev, dtype=torch.int32)
         self.hyper = torch.zeros(4, device=dev, dtype=torch.float32)

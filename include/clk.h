@@ -111,6 +111,16 @@ int clk_gemm_fprop(const void* a, int K, const void* w, const float* bias, void*
 int clk_gemm_fprop_eval(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
                         int relu, const float* bn_scale, const float* bn_shift, long long P, int Npad,
                         clk_stream_t st);
+/* The 1x1 head (models/unet.py:72), nn.CrossEntropyLoss (trainer.py:113,174) [+ the distillation term of
+ * clk_ce_kd_loss] and the head's share of loss.backward() (trainer.py:175) in ONE launch: the logits stay in tensor
+ * memory, z is read once and dz written once.  z bf16 [P][64]; wf bf16 [32][64], wd bf16 [64][64] (clk_pack_w of the
+ * head weight); bias f32[C] or NULL; labels int64[P]; old_logits f32 [P][Cold] or NULL.
+ * dz bf16 [P][64] = gradient w.r.t. z; dw f32 [>=C][64] += dW; dbias f64[>=C] += db; loss_acc f64[2] += {sum CE, sum KL}
+ * (same conventions as clk_ce_kd_loss; gscale folds the 1/P of the mean).  err_flag set on a label outside [0, C). */
+int clk_head_loss_bwd(const void* z, const void* wf, const void* wd, const float* bias, const int64_t* labels,
+                      const float* old_logits, long long P, int Cin, int C, int Cold, float T, float lambda,
+                      float gscale, void* dz, float* dw, double* dbias, double* loss_acc, int* err_flag,
+                      clk_stream_t st);
 /* out fp32 [ld_u][ld_t] += u[P][CU]^T * t[P][CT]  (weight gradient of the GEMMs above) */
 int clk_gemm_wgrad(const void* u, int CU, const void* t, int CT, float* out, int ld_u, int ld_t,
                    long long P, clk_stream_t st);

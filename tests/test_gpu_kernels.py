@@ -335,6 +335,39 @@ def test_fused_ce_kd_loss_forward_backward(ops, P, c, cold):
     assert float(dl[:, c:].float().abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("P,c,cold", [(1000, 21, 0), (4096, 21, 16), (513, 2, 0), (255, 7, 7), (128 * 500 + 3, 21, 16)])
+def test_fused_head_loss_backward_matches_the_separate_ops(ops, P, c, cold):
+    """clk_head_loss_bwd == head GEMM -> nn.CrossEntropyLoss (+ KL) -> autograd of both, in fp32 on the same
+    bf16-rounded operands; the gradient w.r.t. the logits is rounded to bf16 before the two backward GEMMs (as in the
+    unfused path), hence the bf16 tolerance on dz / dW / db."""
+    g = gen(P + c + cold)
+    z = bfr(rnd(g, P, 64))
+    w = bfr(rnd(g, c, 64, scale=0.2))
+    b = rnd(g, c)
+    y = torch.randint(0, c, (P,), generator=g)
+    zo = rnd(g, P, cold, scale=2.0) if cold else None
+    T, lam = 2.0, 0.7
+    wf, wd = ops.pack_head(w.view(c, 64, 1, 1).cuda())
+    loss_acc, dz, dw, db = ops.head_loss_bwd(z.to(torch.bfloat16).cuda(), wf, wd, b.cuda(), y.cuda(), c,
+                                              old_logits=None if zo is None else zo.cuda(), T=T, lam=lam)
+    zr = z.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    logits = zr @ wr.t() + br
+    ce = F.cross_entropy(logits, y, reduction="sum")
+    kd = torch.zeros(())
+    if cold:
+        kd = F.kl_div(F.log_softmax(logits[:, :cold] / T, 1), F.softmax(zo / T, 1), reduction="sum")
+    ((ce + lam * T * T * kd) / P).backward()
+    assert abs(float(loss_acc[0]) - float(ce)) <= 1e-4 * abs(float(ce))
+    if cold:
+        assert abs(float(loss_acc[1]) - float(kd)) <= 1e-3 * abs(float(kd)) + 1e-6
+    assert rel(dz, zr.grad) <= 6e-3
+    assert rel(dw[:c], wr.grad) <= 6e-3
+    assert rel(db[:c], br.grad) <= 6e-3
+    assert float(dw[c:].abs().max()) == 0.0 if c < 64 else True
+
+
 @pytest.mark.parametrize("n,nc", [(100001, 22), (65536, 21), (7, 3), (1, 2), (0, 5)])
 def test_confusion_matrix_bit_exact(ops, n, nc):
     g = gen(n + nc)
