@@ -260,7 +260,7 @@ def run_b200(args):
             e[0] += v[0] / PROF_STEPS
             e[1] += v[1] / PROF_STEPS
     model.engine.use_side_stream = True
-    igemm_names = [k for k in prof if k.startswith(("clk_conv3x3_", "clk_gemm_", "clk_convT2x2_"))]
+    igemm_names = [k for k in prof if k.startswith(("clk_conv3x3_", "clk_gemm_", "clk_convT2x2_", "clk_head_loss_bwd"))]
     igemm_ms = sum(prof[k][1] for k in igemm_names)
     igemm_n = sum(prof[k][0] for k in igemm_names)
     all_ms = sum(v[1] for v in prof.values())

@@ -1568,6 +1568,8 @@ constexpr int kHlThreads = 128;
 constexpr int kHlTile = 128 * 128;                 // [128 px][64 ch] bf16
 constexpr int kHlSmem = 3 * kHlTile + 32 * 128 + 64 * 128 + 8 * 8 + 16 + 1024;
 
+// NC: compile-time bound on the class count (21 = the reference head, 32 = generic); KD: distillation term present
+template <int NC, bool KD>
 __global__ void __launch_bounds__(kHlThreads, 3)
     head_loss_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapWf,
                      const __grid_constant__ CUtensorMap mapWd, const __grid_constant__ HeadLossParams p) {
@@ -1629,8 +1631,14 @@ __global__ void __launch_bounds__(kHlThreads, 3)
   constexpr uint32_t idesc_dw = umma_idesc_bf16(128, 64, 1, 1);
   const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   const float invT = 1.f / p.T;
-  const bool kd_on = p.old_logits != nullptr;
-  float ce_local = 0.f, kd_local = 0.f, db_local = 0.f;
+  const int C = p.C;
+  float ce_local = 0.f, kd_local = 0.f;
+  float g[NC], db_acc[NC], bias_r[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    db_acc[c] = 0.f;
+    bias_r[c] = (c < C && p.bias != nullptr) ? p.bias[c] : 0.f;
+  }
   uint32_t ph = 0;  // phase of mma_bar
   uint32_t it = 0;
   for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
@@ -1647,96 +1655,97 @@ __global__ void __launch_bounds__(kHlThreads, 3)
                   idesc_logits, k != 0 ? 1u : 0u);
       umma_commit(mma_bar);
     }
+    // the label (and the old model's logits) are requested before waiting for the tensor core
+    const long long pix = t * 128 + tid;
+    const bool valid = pix < p.P;
+    const long long y = valid ? p.labels[pix] : 0;
     mbar_wait(mma_bar, ph);
     ph ^= 1;
     tc_fence_after();
     // ---- softmax cross-entropy (+ distillation) on this thread's pixel
-    const long long pix = t * 128 + tid;
-    const bool valid = pix < p.P;
-    float g[32];
     {
       uint32_t v[32];
       tmem_ld32(lane_addr, v);
-      tmem_ld_wait();
-      float z[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) z[c] = __uint_as_float(v[c]) + (c < p.C ? p.bias[c] : 0.f);
-      const long long y = valid ? p.labels[pix] : 0;
-      float mx = -CUDART_INF_F;
-#pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c < p.C) mx = fmaxf(mx, z[c]);
-      float se = 0.f;
-#pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c < p.C) se += __expf(z[c] - mx);
-      const float lse = mx + __logf(se);
-      const float inv_se = 1.f / se;
-      const bool yok = y >= 0 && y < p.C;
-      if (valid && !yok && p.err_flag != nullptr) *p.err_flag = 1;
-      if (valid && yok) {
-        float zy = 0.f;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) zy = (c == y) ? z[c] : zy;
-        ce_local += lse - zy;
-      }
-      float lq = 0.f, lo = 0.f;
-      float zo[32];
-      if (kd_on) {
+      float zo[KD ? NC : 1];
+      if constexpr (KD) {
         const float* orow = p.old_logits + (valid ? pix : 0) * p.Cold;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) zo[c] = (c < p.Cold) ? orow[c] : -CUDART_INF_F;
+      }
+      tmem_ld_wait();
+      float z[NC];
+      float m4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};  // 4 chains: instruction-level parallelism
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        z[c] = (c < C) ? __uint_as_float(v[c]) + bias_r[c] : -CUDART_INF_F;
+        m4[c & 3] = fmaxf(m4[c & 3], z[c]);
+      }
+      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+      float e[NC];
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        e[c] = __expf(z[c] - mx);  // exp(-inf) = 0 for the padding classes
+        s4[c & 3] += e[c];
+      }
+      const float se = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+      const bool yok = y >= 0 && y < C;
+      if (valid && !yok && p.err_flag != nullptr) *p.err_flag = 1;
+      const bool live = valid && yok;
+      const float inv_se = live ? p.gscale / se : 0.f;
+      float zy = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        zy = (c == y) ? z[c] : zy;
+        g[c] = e[c] * inv_se - ((c == y && live) ? p.gscale : 0.f);
+      }
+      if (live) ce_local += mx + __logf(se) - zy;
+      if constexpr (KD) {
+        // q = softmax(z[:Cold] / T), p0 = softmax(zold / T) (same arithmetic as ce_kd_loss_kernel)
         float mq = -CUDART_INF_F, mo = -CUDART_INF_F;
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          zo[c] = (c < p.Cold) ? orow[c] : 0.f;
-          if (c < p.Cold) {
-            mq = fmaxf(mq, z[c] * invT);
-            mo = fmaxf(mo, zo[c] * invT);
-          }
+        for (int c = 0; c < NC; ++c) {
+          z[c] = (c < p.Cold) ? z[c] * invT : -CUDART_INF_F;
+          zo[c] = zo[c] * invT;  // -inf beyond Cold
+          mq = fmaxf(mq, z[c]);
+          mo = fmaxf(mo, zo[c]);
         }
         float sq = 0.f, so = 0.f;
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c < p.Cold) {
-            sq += __expf(z[c] * invT - mq);
-            so += __expf(zo[c] * invT - mo);
-          }
-        lq = mq + __logf(sq);
-        lo = mo + __logf(so);
-      }
-      float kd = 0.f;
+        for (int c = 0; c < NC; ++c) {
+          sq += __expf(z[c] - mq);
+          so += __expf(zo[c] - mo);
+        }
+        const float lq = mq + __logf(sq), lo = mo + __logf(so);
+        const float kscale = valid ? p.lambda * p.T * p.gscale : 0.f;
+        float kd = 0.f;
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        float d = 0.f;
-        if (valid && c < p.C) {
-          d = yok ? (__expf(z[c] - mx) * inv_se - (c == y ? 1.f : 0.f)) : 0.f;
-          if (kd_on && c < p.Cold) {
-            const float logq = z[c] * invT - lq;
-            const float logp0 = zo[c] * invT - lo;
+        for (int c = 0; c < NC; ++c) {
+          if (c < p.Cold) {
+            const float logq = z[c] - lq, logp0 = zo[c] - lo;
             const float p0 = __expf(logp0);
             kd += p0 * (logp0 - logq);
-            d += p.lambda * p.T * (__expf(logq) - p0);
+            g[c] += kscale * (__expf(logq) - p0);
           }
-          d *= p.gscale;
         }
-        g[c] = d;
+        if (valid) kd_local += kd;
       }
-      kd_local += kd;
     }
     // dlogits row -> bf16 -> shared memory in the SWIZZLE_128B pattern TMA would have produced
     {
       uint32_t pk[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(g[2 * j], g[2 * j + 1]);
+      for (int j = 0; j < 16; ++j)
+        pk[j] = (2 * j < NC) ? pack_bf16x2(g[2 * j], (2 * j + 1 < NC) ? g[2 * j + 1] : 0.f) : 0u;
       uint4* row = reinterpret_cast<uint4*>(sD + tid * 128);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
         row[c ^ (tid & 7)] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {  // the bias gradient sums what the tensor core will see (bf16-rounded)
-        g[2 * j] = bf16lo_to_f32(pk[j]);
-        g[2 * j + 1] = bf16hi_to_f32(pk[j]);
+        if (2 * j < NC) db_acc[2 * j] += bf16lo_to_f32(pk[j]);
+        if (2 * j + 1 < NC) db_acc[2 * j + 1] += bf16hi_to_f32(pk[j]);
       }
-      db_local += warp_colsum32(g, lane);
     }
     tc_fence_before();     // the logits were read out of TMEM before the next MMA overwrites them
     fence_proxy_async();   // generic-proxy writes of the dlogits tile -> visible to the tensor core (async proxy)
@@ -1767,23 +1776,27 @@ __global__ void __launch_bounds__(kHlThreads, 3)
         tma_load_5d(sZ + s * kHlTile, &mapZ, &z_full[s], 0, static_cast<int>(tn * 128), 0, 0, 0);
       }
     }
-    // ---- dz row -> bf16 -> global
+    // ---- dz row -> bf16 -> global (both 32-column loads in flight before the first use)
     {
       __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.dz) + (valid ? pix : 0) * 64;
+      uint32_t v0[32], v1[32];
+      tmem_ld32(lane_addr, v0);
+      tmem_ld32(lane_addr + 32, v1);
+      tmem_ld_wait();
+      if (valid) {
+        uint4* o = reinterpret_cast<uint4*>(orow);
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t v[32];
-        tmem_ld32(lane_addr + half * 32, v);
-        tmem_ld_wait();
-        if (valid) {
-          uint4* o = reinterpret_cast<uint4*>(orow + half * 32);
+        for (int j = 0; j < 4; ++j)
+          o[j] = make_uint4(pack_bf16x2(__uint_as_float(v0[8 * j]), __uint_as_float(v0[8 * j + 1])),
+                            pack_bf16x2(__uint_as_float(v0[8 * j + 2]), __uint_as_float(v0[8 * j + 3])),
+                            pack_bf16x2(__uint_as_float(v0[8 * j + 4]), __uint_as_float(v0[8 * j + 5])),
+                            pack_bf16x2(__uint_as_float(v0[8 * j + 6]), __uint_as_float(v0[8 * j + 7])));
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o[j] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                              pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                              pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                              pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-        }
+        for (int j = 0; j < 4; ++j)
+          o[4 + j] = make_uint4(pack_bf16x2(__uint_as_float(v1[8 * j]), __uint_as_float(v1[8 * j + 1])),
+                                pack_bf16x2(__uint_as_float(v1[8 * j + 2]), __uint_as_float(v1[8 * j + 3])),
+                                pack_bf16x2(__uint_as_float(v1[8 * j + 4]), __uint_as_float(v1[8 * j + 5])),
+                                pack_bf16x2(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7])));
       }
     }
     tc_fence_before();
@@ -1799,7 +1812,7 @@ __global__ void __launch_bounds__(kHlThreads, 3)
         uint32_t v[32];
         tmem_ld32(tmem_base + 64 + half * 32, v);
         tmem_ld_wait();
-        if (lane < p.C) {
+        if (lane < C) {
           float* o = p.dw + lane * 64 + half * 32;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -1808,14 +1821,20 @@ __global__ void __launch_bounds__(kHlThreads, 3)
         }
       }
     }
-    if (lane < p.C) atomicAdd(&p.dbias[lane], static_cast<double>(db_local));
+    {  // bias gradient: per-thread sums over this CTA's tiles -> one column sum per warp
+      float f[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) f[c] = (c < NC) ? db_acc[c] : 0.f;
+      const float colsum = warp_colsum32(f, lane);
+      if (lane < C) atomicAdd(&p.dbias[lane], static_cast<double>(colsum));
+    }
     for (int o = 16; o > 0; o >>= 1) {
       ce_local += __shfl_xor_sync(0xffffffffu, ce_local, o);
       kd_local += __shfl_xor_sync(0xffffffffu, kd_local, o);
     }
     if (lane == 0) {
       atomicAdd(p.loss_acc, static_cast<double>(ce_local));
-      if (kd_on) atomicAdd(p.loss_acc + 1, static_cast<double>(kd_local));
+      if (KD) atomicAdd(p.loss_acc + 1, static_cast<double>(kd_local));
     }
   }
   tc_fence_before();
@@ -1823,18 +1842,30 @@ __global__ void __launch_bounds__(kHlThreads, 3)
   if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
-cudaError_t launch_head_loss(const CUtensorMap& z, const CUtensorMap& wf, const CUtensorMap& wd, const HeadLossParams& p,
-                             int num_sms, cudaStream_t st) {
+template <int NC, bool KD>
+static cudaError_t launch_head_loss_t(const CUtensorMap& z, const CUtensorMap& wf, const CUtensorMap& wd,
+                                      const HeadLossParams& p, int num_sms, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(head_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHlSmem);
+    cudaError_t e = cudaFuncSetAttribute(head_loss_kernel<NC, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHlSmem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   long long grid = (p.P + 127) / 128;
   if (grid > 3ll * num_sms) grid = 3ll * num_sms;
-  launch_k(head_loss_kernel, dim3(static_cast<unsigned>(grid)), dim3(kHlThreads), kHlSmem, st, z, wf, wd, p);
+  launch_k(head_loss_kernel<NC, KD>, dim3(static_cast<unsigned>(grid)), dim3(kHlThreads), kHlSmem, st, z, wf, wd, p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_head_loss(const CUtensorMap& z, const CUtensorMap& wf, const CUtensorMap& wd, const HeadLossParams& p,
+                             int num_sms, cudaStream_t st) {
+  const bool kd = p.old_logits != nullptr;
+  if (p.C == 21) {  // the reference head (21 VOC classes): loops unrolled to exactly 21 columns
+    return kd ? launch_head_loss_t<21, true>(z, wf, wd, p, num_sms, st)
+              : launch_head_loss_t<21, false>(z, wf, wd, p, num_sms, st);
+  }
+  return kd ? launch_head_loss_t<32, true>(z, wf, wd, p, num_sms, st)
+            : launch_head_loss_t<32, false>(z, wf, wd, p, num_sms, st);
 }
 
 }  // namespace clk

@@ -1348,6 +1348,49 @@ __device__ __forceinline__ int find_job(const long long* __restrict__ jobs, int 
   return j;
 }
 
+// full 32x32 tile with compile-time T: every global load of a thread is independent and issued before the first
+// use (4*T loads in flight per thread), and the bf16 outputs leave as 16-byte stores (8 rows x 64 B per warp
+// instruction instead of one 64-byte row).  Shared-memory indices are conflict-free (odd pitch).
+template <int T>
+__device__ __forceinline__ void pack_tile_fast(float* tile, const float* __restrict__ src,
+                                               __nv_bfloat16* __restrict__ outAB, __nv_bfloat16* __restrict__ outBA,
+                                               int B, int ldA, int ldB, int ldB2, int ldA2, int rev, int a0, int b0,
+                                               int warp, int lane) {
+  constexpr int pitch = 32 * T + 1;
+  float v[4][T];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float* row = src + (static_cast<long long>(a0 + warp + 8 * r) * B + b0) * T;
+#pragma unroll
+    for (int i = 0; i < T; ++i) v[r][i] = row[lane + 32 * i];
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int i = 0; i < T; ++i) tile[(warp + 8 * r) * pitch + lane + 32 * i] = v[r][i];
+  __syncthreads();
+  const int rr = lane >> 2, c = lane & 3;
+  if (outAB != nullptr) {
+    for (int item = warp; item < 4 * T; item += 8) {
+      const int t = item >> 2, ar = (item & 3) * 8 + rr;
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = tile[ar * pitch + (8 * c + e) * T + t];
+      *reinterpret_cast<uint4*>(outAB + (static_cast<long long>(t) * ldA + a0 + ar) * ldB + b0 + 8 * c) = pack8(f);
+    }
+  }
+  if (outBA != nullptr) {
+    for (int item = warp; item < 4 * T; item += 8) {
+      const int t = item >> 2, br = (item & 3) * 8 + rr;
+      const int tt = rev ? T - 1 - t : t;
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = tile[(8 * c + e) * pitch + br * T + t];
+      *reinterpret_cast<uint4*>(outBA + (static_cast<long long>(tt) * ldB2 + b0 + br) * ldA2 + a0 + 8 * c) = pack8(f);
+    }
+  }
+}
+
 // row: {src, outAB, outBA, A, B, T, ldA, ldB, ldB2, ldA2, rev, tile0, tiles_b, -, -, -}
 __global__ void __launch_bounds__(256) pack_w_multi_kernel(const long long* __restrict__ jobs, int njobs) {
   pdl_launch_dependents();
@@ -1367,6 +1410,16 @@ __global__ void __launch_bounds__(256) pack_w_multi_kernel(const long long* __re
   const int na = min(32, A - a0), nb = min(32, B - b0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int pitch = 32 * T + 1;
+  const bool vec_ok = na == 32 && nb == 32 && (ldB % 8) == 0 && (ldA2 % 8) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(outAB) | reinterpret_cast<uintptr_t>(outBA)) & 15) == 0;
+  if (vec_ok && T == 9) {
+    pack_tile_fast<9>(tile, src, outAB, outBA, B, ldA, ldB, ldB2, ldA2, rev, a0, b0, warp, lane);
+    return;
+  }
+  if (vec_ok && T == 4) {
+    pack_tile_fast<4>(tile, src, outAB, outBA, B, ldA, ldB, ldB2, ldA2, rev, a0, b0, warp, lane);
+    return;
+  }
   for (int ar = warp; ar < na; ar += 8) {
     const float* row = src + (static_cast<long long>(a0 + ar) * B + b0) * T;
     for (int rem = lane; rem < nb * T; rem += 32) tile[ar * pitch + rem] = row[rem];
@@ -1396,6 +1449,39 @@ cudaError_t pack_w_multi(const void* jobs, int njobs, int total_tiles, int max_T
   return cudaGetLastError();
 }
 
+// conv3x3 case ([T][ldB][ldA] -> [A][B][T]), full tile: 4*T independent loads per thread in flight
+template <int T>
+__device__ __forceinline__ void unpack_tile_fast(float* tile, const float* __restrict__ D, float* __restrict__ grad,
+                                                 int B, int ldA, int ldB, float alpha, int accumulate, int a0, int b0,
+                                                 int warp, int lane) {
+  constexpr int pitch = 32 * T + 1;
+  float v[4][T];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int t = 0; t < T; ++t)
+      v[r][t] = D[(static_cast<long long>(t) * ldB + b0 + warp + 8 * r) * ldA + a0 + lane];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int t = 0; t < T; ++t) tile[lane * pitch + (warp + 8 * r) * T + t] = v[r][t];
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float* row = grad + (static_cast<long long>(a0 + warp + 8 * r) * B + b0) * T;
+    float old[T];
+    if (accumulate) {
+#pragma unroll
+      for (int i = 0; i < T; ++i) old[i] = row[lane + 32 * i];
+    }
+#pragma unroll
+    for (int i = 0; i < T; ++i) {
+      const float x = alpha * tile[(warp + 8 * r) * pitch + lane + 32 * i];
+      row[lane + 32 * i] = accumulate ? old[i] + x : x;
+    }
+  }
+}
+
 // row: {D, grad, A, B, T, ldA, ldB, alpha (double bits), accumulate, tile0, tiles_b, ...}
 __global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const long long* __restrict__ jobs, int njobs) {
   pdl_launch_dependents();
@@ -1418,6 +1504,10 @@ __global__ void __launch_bounds__(256) unpack_wgrad_multi_kernel(const long long
   const int pitch = 32 * T + 1;
   const int nsplit = static_cast<int>(J[12]) > 0 ? static_cast<int>(J[12]) : 1;  // split-K partial buffers to sum
   const long long sstride = J[13];
+  if (transposed && nsplit == 1 && na == 32 && nb == 32 && T == 9) {
+    unpack_tile_fast<9>(tile, D, grad, B, ldA, ldB, alpha, accumulate, a0, b0, warp, lane);
+    return;
+  }
   if (transposed) {
     for (int t = 0; t < T; ++t)
       for (int br = warp; br < nb; br += 8)

@@ -113,15 +113,30 @@ def main():
         s1 = torch.zeros(64, device=dev, dtype=torch.float64)
         return lambda: ops.bn_bwd_reduce(dz, y, s1, s1.clone())
 
+    @case("head_loss")
+    def _():
+        z = t(B, S, S, 64)
+        wf, wd = t(32, 64), t(64, 64)
+        b = torch.zeros(21, device=dev)
+        y = torch.randint(0, 21, (B, S, S), device=dev)
+        dz = torch.empty_like(z)
+        dw = torch.zeros(64, 64, device=dev)
+        db = torch.zeros(64, device=dev, dtype=torch.float64)
+        la = torch.zeros(2, device=dev, dtype=torch.float64)
+        return lambda: ops.head_loss_bwd(z, wf, wd, b, y, 21, dz=dz, dw=dw, dbias=db, loss_acc=la)
+
     for name, make in cases.items():
         if want and name not in want:
             continue
         fn = make()
         fn()
         torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         fn()
+        e1.record()
         torch.cuda.synchronize()
-        print("ran", name, flush=True)
+        print(f"ran {name}: {e0.elapsed_time(e1) * 1e3:.1f} us", flush=True)
 
 
 if __name__ == "__main__":
