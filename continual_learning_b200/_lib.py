@@ -121,6 +121,10 @@ def ensure_device(dev=None):
     if dev not in _checked_devices:
         check(load().clk_query_device(dev))
         _checked_devices.add(dev)
+        # developer override of the library's tuning knobs: CLK_TUNING="pdl=0,conv3_v2=2"
+        for item in filter(None, os.environ.get("CLK_TUNING", "").split(",")):
+            k, v = item.split("=")
+            set_tuning(k.strip(), int(v))
     return dev
 
 

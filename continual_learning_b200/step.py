@@ -7,6 +7,8 @@ This is the public fast path (`bench.py` e2e goes through `TrainStep.step_host`)
 nn.Module path (UNet + CrossEntropyDistillLoss + FusedAdam driven by the reference Trainer) launches
 exactly the same kernels through autograd.
 """
+import os
+
 import torch
 
 from . import ops
@@ -23,7 +25,8 @@ class TrainStep:
         # B200 x2 (torch 2.11 / NCCL 2.28.9), and the eager step is GPU-bound anyway (7.28 vs 7.0 ms at N=2 vs 1)
         self.use_graph = use_graph and comm is None
         # head GEMM + loss + head backward as one kernel (needs the reference geometry: 64 channels, <= 32 classes)
-        self.fused_head = model.conv_dim == 64 and model.num_classes <= 32
+        self.fused_head = (model.conv_dim == 64 and model.num_classes <= 32
+                           and os.environ.get("CLK_FUSED_HEAD", "1") != "0")
         self.comm = comm  # parallel.GradAllReduce or None
         self.graph = None
         self.shape = None
@@ -133,12 +136,17 @@ class TrainStep:
             loss = loss + (self.lam * self.T * self.T / self.npix) * self.loss_acc[1]
         return loss
 
-    def step_host(self, x_pinned, y_pinned, prefetch=None):
+    def step_host(self, x_pinned, y_pinned, prefetch=None, defer_loss=False):
         """end-to-end step from pinned HOST tensors: H2D of the inputs, the step, D2H of the loss (float).
 
         `prefetch=(x_next, y_next)` starts the H2D copy of the NEXT batch on a copy stream before this step's
         kernels are launched, so the PCIe transfer overlaps the compute (every batch is still copied exactly
-        once, inside the caller's loop); the next call recognises its staged inputs and skips the copy."""
+        once, inside the caller's loop); the next call recognises its staged inputs and skips the copy.
+
+        `defer_loss=True` keeps the host one step ahead of the device: the loss of this step is copied to pinned host
+        memory asynchronously and RETURNED BY THE NEXT CALL (the first call returns None; `flush_loss()` returns the
+        last one).  Every step's loss is still read back, but the device never idles waiting for the host to
+        launch the next step."""
         dev = next(self.model.parameters()).device
         staged = getattr(self, "_staged", None)
         if staged is not None and staged[0] is x_pinned and staged[1] is y_pinned:
@@ -160,7 +168,29 @@ class TrainStep:
         loss = self.step(x, y)
         x.record_stream(torch.cuda.current_stream())
         y.record_stream(torch.cuda.current_stream())
-        return float(loss.item())
+        if not defer_loss:
+            return float(loss.item())
+        if getattr(self, "_loss_host", None) is None:
+            self._loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
+            self._loss_ev = [None, None]
+            self._loss_k = 0
+        prev = self.flush_loss()
+        k = self._loss_k & 1
+        self._loss_host[k].copy_(loss.reshape(1), non_blocking=True)
+        self._loss_ev[k] = torch.cuda.Event()
+        self._loss_ev[k].record()
+        self._loss_pending = k
+        self._loss_k += 1
+        return prev
+
+    def flush_loss(self):
+        """the loss of the most recent `step_host(defer_loss=True)` call that has not been returned yet (or None)."""
+        k = getattr(self, "_loss_pending", None)
+        if k is None:
+            return None
+        self._loss_ev[k].synchronize()
+        self._loss_pending = None
+        return float(self._loss_host[k][0])
 
     # the capture warm-up and the capture itself run the step body for real: undo their effect on the
     # parameters, optimiser state and BatchNorm buffers so that step k of a graph run equals step k eagerly

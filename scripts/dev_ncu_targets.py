@@ -113,6 +113,19 @@ def main():
         s1 = torch.zeros(64, device=dev, dtype=torch.float64)
         return lambda: ops.bn_bwd_reduce(dz, y, s1, s1.clone())
 
+    @case("bn_apply")
+    def _():
+        y = t(B, S, S, 64)
+        k = torch.ones(64, device=dev)
+        out = torch.empty_like(y)
+        return lambda: ops.bn_apply(y, k, k, out=out)
+
+    @case("bn_apply_pool")
+    def _():
+        y = t(B, S, S, 64)
+        k = torch.ones(64, device=dev)
+        return lambda: ops.bn_apply_pool(y, k, k)
+
     @case("head_loss")
     def _():
         z = t(B, S, S, 64)

@@ -277,3 +277,31 @@ def test_checkpoint_interchange_with_reference_layout(clk, tmp_path):
     with torch.no_grad():
         m2.eval()
         assert torch.isfinite(m2(x.cuda())).all()
+
+
+def test_step_host_pinned_inputs_prefetch_and_deferred_loss(clk):
+    """the end-to-end entry point bench.py times: pinned host batches in, loss out; prefetching the next batch and
+    reading the loss one step late must not change a single number of the trajectory."""
+    sd = make_state_dict(5)
+    batches = [structured_batch(200 + i, 2, 64, 64) for i in range(4)]
+    pinned = [(bx.pin_memory(), by.pin_memory()) for bx, by in batches]
+    runs = []
+    for mode in ("device", "host", "host_prefetch_deferred"):
+        m = make_model(clk, sd)
+        ts = clk.TrainStep(m, clk.FusedAdam(m.parameters(), lr=1e-4, betas=(0.5, 0.99)), use_graph=True)
+        if mode == "device":
+            losses = [float(ts.step(bx.cuda(), by.cuda())) for bx, by in batches]
+        elif mode == "host":
+            losses = [ts.step_host(bx, by) for bx, by in pinned]
+        else:
+            got = []
+            for i, (bx, by) in enumerate(pinned):
+                nxt = pinned[i + 1] if i + 1 < len(pinned) else None
+                got.append(ts.step_host(bx, by, prefetch=nxt, defer_loss=True))
+            assert got[0] is None  # nothing to return yet: the host runs one step ahead
+            losses = got[1:] + [ts.flush_loss()]
+            assert ts.flush_loss() is None
+        runs.append(losses)
+    # same kernels, same order: only the fp32 atomics of the weight gradients reorder sums between runs
+    np.testing.assert_allclose(runs[0], runs[1], rtol=5e-3)
+    np.testing.assert_allclose(runs[0], runs[2], rtol=5e-3)
