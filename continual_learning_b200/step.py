@@ -21,7 +21,7 @@ class TrainStep:
             raise TypeError("TrainStep needs continual_learning_b200.FusedAdam")
         self.model, self.opt, self.old = model, optimizer, old_model
         self.T, self.lam = float(T), float(lam)
-        # with a communicator the step runs eagerly: capturing the NCCL all-reduces into the graph hung on
+        # with a communicator the step runs eagerly: capturing the NCCL all-reduces into the graph hung (twice, global and thread_local capture modes) on
         # B200 x2 (torch 2.11 / NCCL 2.28.9), and the eager step is GPU-bound anyway (7.28 vs 7.0 ms at N=2 vs 1)
         self.use_graph = use_graph and comm is None
         # head GEMM + loss + head backward as one kernel (needs the reference geometry: 64 channels, <= 32 classes)
