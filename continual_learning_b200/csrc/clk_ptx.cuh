@@ -289,6 +289,19 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 
 extern int g_pdl;  // api.cu, tuning key "pdl"
 
+// cudaFuncSetAttribute applies to the current device only: one flag per device ordinal
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool first() {
+    int d = 0;
+    cudaGetDevice(&d);
+    d &= 63;
+    if (done[d]) return false;
+    done[d] = true;
+    return true;
+  }
+};
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                             Args&&... args) {

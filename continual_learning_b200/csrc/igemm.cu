@@ -656,11 +656,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 cudaError_t launch_wgrad9(const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
                           const Wgrad9Params& p, cudaStream_t st) {
   const int smem = kW9Stages * kW9StageBytes + (2 * kW9Stages + 1) * 8 + 16 + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(igemm_wgrad9_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   dim3 grid(p.cin_slabs * p.cout_tiles, p.ksplit);
   launch_k(igemm_wgrad9_kernel, dim3(grid), dim3(kThreads), smem, st, u, t0, t1, p);
@@ -820,11 +819,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 cudaError_t launch_wgrad9x2(const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
                             const Wgrad9Params& p, cudaStream_t st) {
   const int smem = kW2Stages * kW2StageBytes + 2048 + (2 * kW2Stages + 1) * 8 + 16 + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(igemm_wgrad9x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   dim3 grid(2 * p.cin_slabs * p.cout_tiles, p.ksplit);  // cout_tiles = Cout / 128 here
   launch_k(igemm_wgrad9x2_kernel, dim3(grid), dim3(kThreads), smem, st, u, t0, t1, p);
@@ -1128,11 +1126,10 @@ template <int BN>
 static cudaError_t launch_conv3_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                                   const Conv3Params& p, int num_sms, cudaStream_t st) {
   constexpr int smem = C3Cfg<BN>::Smem;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(igemm_conv3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   int grid = p.m_tiles * p.n_tiles;
   if (grid > num_sms) grid = num_sms;
@@ -1459,11 +1456,10 @@ template <int BN, int SUB>
 static cudaError_t launch_conv3x2_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                                     const Conv3Params& p, int num_sms, cudaStream_t st) {
   constexpr int smem = X2Cfg<BN, SUB>::Smem;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(igemm_conv3x2_kernel<BN, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   int clusters = p.m_tiles * p.n_tiles;
   if (clusters > num_sms / 2) clusters = num_sms / 2;
@@ -1493,12 +1489,11 @@ static cudaError_t launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1,
                                   const CUtensorMap& b, const FpropParams& p, int m_tiles,
                                   int n_tiles, cudaStream_t st) {
   constexpr int smem = fprop_smem_bytes<BN, STAGES>();
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(igemm_fprop_kernel<BN, STAGES, OutT>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   int grid = m_tiles * n_tiles;
   const int cap = g_fprop_sms * (smem <= 113 * 1024 ? 2 : 1);  // resident CTAs per SM by shared memory
@@ -1533,12 +1528,11 @@ static cudaError_t launch_wgrad_t(const CUtensorMap& u, const CUtensorMap& t0,
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(p.G * BN)) cols <<= 1;
   if (cols > 512) return cudaErrorInvalidValue;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(igemm_wgrad_kernel<BN>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   dim3 grid(p.m_tiles * p.n_tiles * p.tap_groups, p.ksplit);
   launch_k(igemm_wgrad_kernel<BN>, dim3(grid), dim3(kThreads), smem, st, u, t0, t1, p, stages, cols);
@@ -1845,11 +1839,10 @@ __global__ void __launch_bounds__(kHlThreads, 3)
 template <int NC, bool KD>
 static cudaError_t launch_head_loss_t(const CUtensorMap& z, const CUtensorMap& wf, const CUtensorMap& wd,
                                       const HeadLossParams& p, int num_sms, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaError_t e = cudaFuncSetAttribute(head_loss_kernel<NC, KD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kHlSmem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   long long grid = (p.P + 127) / 128;
   if (grid > 3ll * num_sms) grid = 3ll * num_sms;

@@ -896,10 +896,9 @@ cudaError_t ce_kd_loss(const float* logits, const float* old_logits, const long 
                        double* loss_acc, int* err_flag, cudaStream_t st) {
   const size_t smem = static_cast<size_t>(kLossPix) * (C + (old_logits ? Cold : 0)) * sizeof(float);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncSetAttribute(ce_kd_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr = true;
   }
   launch_k(ce_kd_loss_kernel, dim3(grid_for(P, kLossPix, 4)), dim3(kLossPix), smem, st, 
       logits, old_logits, labels, P, C, Cold, T, lambda, gscale, static_cast<__nv_bfloat16*>(dlogits), ldd,
@@ -1018,10 +1017,9 @@ cudaError_t argmax_confusion(const float* logits, const long long* labels, long 
   const size_t smem = static_cast<size_t>(kHistThreads / 32) * nc * nc * sizeof(unsigned int) +
                       static_cast<size_t>(kHistThreads) * C * sizeof(float);
   if (smem > 96 * 1024) return cudaErrorInvalidValue;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
     cudaFuncSetAttribute(argmax_confusion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr = true;
   }
   launch_k(argmax_confusion_kernel, dim3(grid_for(P, kHistThreads * 4, 4)), dim3(kHistThreads), smem, st, 
       logits, labels, P, C, nc, pred_out, reinterpret_cast<unsigned long long*>(conf),
