@@ -1554,231 +1554,307 @@ cudaError_t launch_wgrad(int BN, const CUtensorMap& u, const CUtensorMap& t0, co
 //   CE (+ temperature-KL)      one thread per pixel on its TMEM row; dlogits -> bf16 -> shared memory (swizzled)
 //   dz = dlogits Wd            tcgen05, A = the dlogits tile just written           -> bf16 [P][64]
 //   dW += dlogits^T z          tcgen05, the SAME two tiles read MN-major, accumulated in TMEM over the CTA's tiles
-//   db += colsum(dlogits)      warp shuffles
+//   db += colsum(dlogits)      per-thread sums, one warp-shuffle column sum per CTA
 // HBM traffic: z read once, dz written once, labels (+ old logits) read once: 276 B/pixel instead of ~1.2 KB/pixel
-// for the five separate launches.  128 threads per CTA (thread = pixel = TMEM lane), three CTAs per SM hide the
-// per-tile dependency chain (MMA -> CE -> MMA -> store); thread 0 issues TMA and MMAs.
-constexpr int kHlThreads = 128;
+// for the five separate launches.
+// One persistent CTA per SM, 16 warps, software pipeline over 128-pixel tiles:
+//   warp 0      TMA producer (z tiles, 4 stages)          warp 1   MMA issuer + TMEM owner
+//   warps 4-7   loss group 0 (even tiles)                  warps 8-11  loss group 1 (odd tiles)
+//   warps 12-15 dz store group (every tile)
+// Tile i uses buffer b = i & 1 of the logits / dlogits / dz buffers, so loss group g always works on buffer g; the
+// issuer runs logits(i+2) ahead of dz(i), and the loss of tile i+1 overlaps the dz store of tile i.
+constexpr int kHlThreads = 512;
+constexpr int kHlStages = 4;
 constexpr int kHlTile = 128 * 128;                 // [128 px][64 ch] bf16
-constexpr int kHlSmem = 3 * kHlTile + 32 * 128 + 64 * 128 + 8 * 8 + 16 + 1024;
+constexpr int kHlBars = 2 * kHlStages + 1 + 12;
+constexpr int kHlSmem = (2 + kHlStages) * kHlTile + 32 * 128 + 64 * 128 + kHlBars * 8 + 16 + 1024;
+constexpr uint32_t kHlTmemCols = 256;              // logits 2 x 32 | dz 2 x 64 | dW 64
+
+// softmax cross-entropy (+ distillation) of one pixel: v = the 32 fp32 accumulators of its TMEM row.
+// g[c] = gradient w.r.t. logit c (already scaled by gscale); same arithmetic as ce_kd_loss_kernel.
+template <int NC, bool KD>
+__device__ __forceinline__ void head_ce_row(const uint32_t (&v)[32], const float (&zo_in)[KD ? NC : 1], long long y,
+                                            bool valid, const HeadLossParams& p, const float (&bias_r)[NC], float invT,
+                                            float (&g)[NC], float& ce_local, float& kd_local) {
+  const int C = p.C;
+  float z[NC];
+  float m4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};  // 4 chains: instruction-level parallelism
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    z[c] = (c < C) ? __uint_as_float(v[c]) + bias_r[c] : -CUDART_INF_F;
+    m4[c & 3] = fmaxf(m4[c & 3], z[c]);
+  }
+  const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  float e[NC];
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    e[c] = __expf(z[c] - mx);  // exp(-inf) = 0 for the padding classes
+    s4[c & 3] += e[c];
+  }
+  const float se = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  const bool yok = y >= 0 && y < C;
+  if (valid && !yok && p.err_flag != nullptr) *p.err_flag = 1;
+  const bool live = valid && yok;
+  const float inv_se = live ? p.gscale / se : 0.f;
+  float zy = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    zy = (c == y) ? z[c] : zy;
+    g[c] = e[c] * inv_se - ((c == y && live) ? p.gscale : 0.f);
+  }
+  if (live) ce_local += mx + __logf(se) - zy;
+  if constexpr (KD) {
+    // q = softmax(z[:Cold] / T), p0 = softmax(zold / T)
+    float zo[NC];
+    float mq = -CUDART_INF_F, mo = -CUDART_INF_F;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      z[c] = (c < p.Cold) ? z[c] * invT : -CUDART_INF_F;
+      zo[c] = zo_in[c] * invT;  // -inf beyond Cold
+      mq = fmaxf(mq, z[c]);
+      mo = fmaxf(mo, zo[c]);
+    }
+    float sq = 0.f, so = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      sq += __expf(z[c] - mq);
+      so += __expf(zo[c] - mo);
+    }
+    const float lq = mq + __logf(sq), lo = mo + __logf(so);
+    const float kscale = valid ? p.lambda * p.T * p.gscale : 0.f;
+    float kd = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if (c < p.Cold) {
+        const float logq = z[c] - lq, logp0 = zo[c] - lo;
+        const float p0 = __expf(logp0);
+        kd += p0 * (logp0 - logq);
+        g[c] += kscale * (__expf(logq) - p0);
+      }
+    }
+    if (valid) kd_local += kd;
+  }
+}
 
 // NC: compile-time bound on the class count (21 = the reference head, 32 = generic); KD: distillation term present
 template <int NC, bool KD>
-__global__ void __launch_bounds__(kHlThreads, 3)
+__global__ void __launch_bounds__(kHlThreads, 1)
     head_loss_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapWf,
                      const __grid_constant__ CUtensorMap mapWd, const __grid_constant__ HeadLossParams p) {
-  pdl_launch_dependents();
+  if (d_pdl_mode == 0) pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
-  uint8_t* sD = smem;                       // dlogits tile [128 px][64 cls] bf16, SWIZZLE_128B rows
-  uint8_t* sZ = smem + kHlTile;             // two z stages (the first doubles as the ignored upper half of M in dW)
-  uint8_t* sWf = sZ + 2 * kHlTile;          // [32 cls][64 ch]
-  uint8_t* sWd = sWf + 32 * 128;            // [64 ch][64 cls]
+  uint8_t* sD = smem;                          // 2 x dlogits tile [128 px][64 cls] bf16, SWIZZLE_128B rows
+  uint8_t* sZ = smem + 2 * kHlTile;            // z stages (whatever follows a dlogits tile is the ignored upper half of M in dW)
+  uint8_t* sWf = sZ + kHlStages * kHlTile;     // [32 cls][64 ch]
+  uint8_t* sWd = sWf + 32 * 128;               // [64 ch][64 cls]
   uint64_t* z_full = reinterpret_cast<uint64_t*>(sWd + 64 * 128);
-  uint64_t* w_full = z_full + 2;
-  uint64_t* mma_bar = w_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  uint64_t* z_empty = z_full + kHlStages;
+  uint64_t* w_full = z_empty + kHlStages;
+  uint64_t* lg_full = w_full + 1;    // [2] logits ready           (tcgen05.commit)
+  uint64_t* lg_empty = lg_full + 2;  // [2] logits read out         (4 warps)
+  uint64_t* d_full = lg_empty + 2;   // [2] dlogits tile written    (4 warps)
+  uint64_t* d_empty = d_full + 2;    // [2] dlogits tile consumed   (tcgen05.commit)
+  uint64_t* dz_full = d_empty + 2;   // [2] dz ready                (tcgen05.commit)
+  uint64_t* dz_empty = dz_full + 2;  // [2] dz read out             (4 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dz_empty + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long tiles = (p.P + 127) / 128;
+  const uint32_t n_local = blockIdx.x < tiles ? static_cast<uint32_t>((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
   if (tid == 0) {
-    mbar_init(&z_full[0], 1);
-    mbar_init(&z_full[1], 1);
+    for (int s = 0; s < kHlStages; ++s) {
+      mbar_init(&z_full[s], 1);
+      mbar_init(&z_empty[s], 1);
+    }
     mbar_init(w_full, 1);
-    mbar_init(mma_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&lg_full[b], 1);
+      mbar_init(&lg_empty[b], 4);
+      mbar_init(&d_full[b], 4);
+      mbar_init(&d_empty[b], 1);
+      mbar_init(&dz_full[b], 1);
+      mbar_init(&dz_empty[b], 4);
+    }
     fence_mbar_init();
     tma_prefetch_desc(&mapZ);
     tma_prefetch_desc(&mapWf);
     tma_prefetch_desc(&mapWd);
   }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, 128);
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kHlTmemCols);
     tmem_relinquish();
   }
-  // the zero half of this thread's dlogits row (classes 32..63) is written once
-  {
+  if (tid < 256) {  // the zero half of every dlogits row (classes 32..63) is written once
     uint4* row = reinterpret_cast<uint4*>(sD + tid * 128);
 #pragma unroll
     for (int c = 4; c < 8; ++c) row[c ^ (tid & 7)] = make_uint4(0u, 0u, 0u, 0u);
   }
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
-  if (tid == 0) {
-    mbar_arrive_expect_tx(w_full, 32 * 128 + 64 * 128);
-    tma_load_3d(sWf, &mapWf, w_full, 0, 0, 0);
-    tma_load_3d(sWd, &mapWd, w_full, 0, 0, 0);
-    for (int s = 0; s < 2; ++s) {
-      const long long t = static_cast<long long>(blockIdx.x) + static_cast<long long>(s) * gridDim.x;
-      if (t < tiles) {
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_full, 32 * 128 + 64 * 128);
+      tma_load_3d(sWf, &mapWf, w_full, 0, 0, 0);
+      tma_load_3d(sWd, &mapWd, w_full, 0, 0, 0);
+      for (uint32_t i = 0; i < n_local; ++i) {
+        const uint32_t s = i % kHlStages, k = i / kHlStages;
+        mbar_wait(&z_empty[s], (k & 1) ^ 1);
         mbar_arrive_expect_tx(&z_full[s], kHlTile);
+        const long long t = blockIdx.x + static_cast<long long>(i) * gridDim.x;
         tma_load_5d(sZ + s * kHlTile, &mapZ, &z_full[s], 0, static_cast<int>(t * 128), 0, 0, 0);
       }
     }
-  }
-
-  constexpr uint32_t idesc_logits = umma_idesc_bf16(128, 32, 0, 0);
-  constexpr uint32_t idesc_dz = umma_idesc_bf16(128, 64, 0, 0);
-  constexpr uint32_t idesc_dw = umma_idesc_bf16(128, 64, 1, 1);
-  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-  const float invT = 1.f / p.T;
-  const int C = p.C;
-  float ce_local = 0.f, kd_local = 0.f;
-  float g[NC], db_acc[NC], bias_r[NC];
+    __syncwarp();
+    if (d_pdl_mode == 1) pdl_launch_dependents();
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (elect_one() && n_local > 0) {
+      constexpr uint32_t idesc_logits = umma_idesc_bf16(128, 32, 0, 0);
+      constexpr uint32_t idesc_dz = umma_idesc_bf16(128, 64, 0, 0);
+      constexpr uint32_t idesc_dw = umma_idesc_bf16(128, 64, 1, 1);
+      const uint32_t wf = smem_u32(sWf), wd = smem_u32(sWd);
+      mbar_wait(w_full, 0);
+      auto logits = [&](uint32_t i) {  // logits[128][32] = Z[128][64] Wf^T
+        const uint32_t b = i & 1, k = i >> 1, s = i % kHlStages;
+        mbar_wait(&z_full[s], (i / kHlStages) & 1);
+        mbar_wait(&lg_empty[b], (k & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t zaddr = smem_u32(sZ + s * kHlTile);
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    db_acc[c] = 0.f;
-    bias_r[c] = (c < C && p.bias != nullptr) ? p.bias[c] : 0.f;
-  }
-  uint32_t ph = 0;  // phase of mma_bar
-  uint32_t it = 0;
-  for (long long t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
-    const uint32_t s = it & 1;
-    const uint32_t zaddr = smem_u32(sZ + s * kHlTile);
-    // ---- logits[128][32] = Z[128][64] Wf^T
-    if (tid == 0) {
-      if (it == 0) mbar_wait(w_full, 0);
-      mbar_wait(&z_full[s], (it >> 1) & 1);
-      tc_fence_after();
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem_base + 32 * b, umma_smem_desc(zaddr + kk * 32, 16, 1024), umma_smem_desc(wf + kk * 32, 16, 1024),
+                    idesc_logits, kk != 0 ? 1u : 0u);
+        umma_commit(&lg_full[b]);
+      };
+      logits(0);
+      if (n_local > 1) logits(1);
+      for (uint32_t i = 0; i < n_local; ++i) {
+        // logits of tile i + 2 first: its buffer is free as soon as the loss group has READ the logits of tile i, so the
+        // MMA round trip overlaps the loss arithmetic of tile i instead of sitting between two tiles of that group
+        if (i + 2 < n_local) logits(i + 2);
+        const uint32_t b = i & 1, k = i >> 1, s = i % kHlStages;
+        mbar_wait(&d_full[b], k & 1);
+        mbar_wait(&dz_empty[b], (k & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t daddr = smem_u32(sD + b * kHlTile);
+        const uint32_t zaddr = smem_u32(sZ + s * kHlTile);
+        // dz[128][64] = D[128][32] Wd^T
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem_base, umma_smem_desc(zaddr + k * 32, 16, 1024), umma_smem_desc(smem_u32(sWf) + k * 32, 16, 1024),
-                  idesc_logits, k != 0 ? 1u : 0u);
-      umma_commit(mma_bar);
+        for (int kk = 0; kk < 2; ++kk)
+          umma_bf16(tmem_base + 64 + 64 * b, umma_smem_desc(daddr + kk * 32, 16, 1024),
+                    umma_smem_desc(wd + kk * 32, 16, 1024), idesc_dz, kk != 0 ? 1u : 0u);
+        // dW[cls][ch] += D^T Z through MN-major views of the same two tiles: A = D^T (M = class; rows 64..127 of M
+        // read the 16 KB after the tile and are never used), B = Z (N = channel), K = 128 pixels in 8 steps of 16 rows
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_bf16(tmem_base + 192, umma_smem_desc(daddr + kk * 2048, kHlTile, 1024),
+                    umma_smem_desc(zaddr + kk * 2048, kHlTile, 1024), idesc_dw, (i | kk) != 0 ? 1u : 0u);
+        umma_commit(&dz_full[b]);
+        umma_commit(&d_empty[b]);
+        umma_commit(&z_empty[s]);
+      }
     }
-    // the label (and the old model's logits) are requested before waiting for the tensor core
-    const long long pix = t * 128 + tid;
-    const bool valid = pix < p.P;
-    const long long y = valid ? p.labels[pix] : 0;
-    mbar_wait(mma_bar, ph);
-    ph ^= 1;
-    tc_fence_after();
-    // ---- softmax cross-entropy (+ distillation) on this thread's pixel
-    {
-      uint32_t v[32];
-      tmem_ld32(lane_addr, v);
+    __syncwarp();
+  } else if (warp >= 4 && warp < 12) {
+    // ------------------------------------------------ loss groups: thread = pixel = TMEM lane
+    const uint32_t grp = (warp - 4) >> 2;  // = buffer index
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 32 * grp;
+    uint8_t* dtile = sD + grp * kHlTile;
+    const float invT = 1.f / p.T;
+    float ce_local = 0.f, kd_local = 0.f;
+    float g[NC], db_acc[NC], bias_r[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      db_acc[c] = 0.f;
+      bias_r[c] = (c < p.C && p.bias != nullptr) ? p.bias[c] : 0.f;
+    }
+    for (uint32_t i = grp; i < n_local; i += 2) {
+      const uint32_t k = i >> 1;
+      const long long t = blockIdx.x + static_cast<long long>(i) * gridDim.x;
+      const long long pix = t * 128 + row;
+      const bool valid = pix < p.P;
+      // the label (and the old model's logits) are requested before waiting for the tensor core
+      const long long y = valid ? p.labels[pix] : 0;
       float zo[KD ? NC : 1];
       if constexpr (KD) {
         const float* orow = p.old_logits + (valid ? pix : 0) * p.Cold;
 #pragma unroll
         for (int c = 0; c < NC; ++c) zo[c] = (c < p.Cold) ? orow[c] : -CUDART_INF_F;
       }
+      mbar_wait(&lg_full[grp], k & 1);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(lane_addr, v);
       tmem_ld_wait();
-      float z[NC];
-      float m4[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};  // 4 chains: instruction-level parallelism
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        z[c] = (c < C) ? __uint_as_float(v[c]) + bias_r[c] : -CUDART_INF_F;
-        m4[c & 3] = fmaxf(m4[c & 3], z[c]);
-      }
-      const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-      float e[NC];
-      float s4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        e[c] = __expf(z[c] - mx);  // exp(-inf) = 0 for the padding classes
-        s4[c & 3] += e[c];
-      }
-      const float se = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-      const bool yok = y >= 0 && y < C;
-      if (valid && !yok && p.err_flag != nullptr) *p.err_flag = 1;
-      const bool live = valid && yok;
-      const float inv_se = live ? p.gscale / se : 0.f;
-      float zy = 0.f;
-#pragma unroll
-      for (int c = 0; c < NC; ++c) {
-        zy = (c == y) ? z[c] : zy;
-        g[c] = e[c] * inv_se - ((c == y && live) ? p.gscale : 0.f);
-      }
-      if (live) ce_local += mx + __logf(se) - zy;
-      if constexpr (KD) {
-        // q = softmax(z[:Cold] / T), p0 = softmax(zold / T) (same arithmetic as ce_kd_loss_kernel)
-        float mq = -CUDART_INF_F, mo = -CUDART_INF_F;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          z[c] = (c < p.Cold) ? z[c] * invT : -CUDART_INF_F;
-          zo[c] = zo[c] * invT;  // -inf beyond Cold
-          mq = fmaxf(mq, z[c]);
-          mo = fmaxf(mo, zo[c]);
-        }
-        float sq = 0.f, so = 0.f;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          sq += __expf(z[c] - mq);
-          so += __expf(zo[c] - mo);
-        }
-        const float lq = mq + __logf(sq), lo = mo + __logf(so);
-        const float kscale = valid ? p.lambda * p.T * p.gscale : 0.f;
-        float kd = 0.f;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          if (c < p.Cold) {
-            const float logq = z[c] - lq, logp0 = zo[c] - lo;
-            const float p0 = __expf(logp0);
-            kd += p0 * (logp0 - logq);
-            g[c] += kscale * (__expf(logq) - p0);
-          }
-        }
-        if (valid) kd_local += kd;
-      }
-    }
-    // dlogits row -> bf16 -> shared memory in the SWIZZLE_128B pattern TMA would have produced
-    {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&lg_empty[grp]);  // the issuer may compute the logits of tile i + 2
+      head_ce_row<NC, KD>(v, zo, y, valid, p, bias_r, invT, g, ce_local, kd_local);
+      // dlogits row -> bf16 -> shared memory in the SWIZZLE_128B pattern TMA would have produced
       uint32_t pk[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         pk[j] = (2 * j < NC) ? pack_bf16x2(g[2 * j], (2 * j + 1 < NC) ? g[2 * j + 1] : 0.f) : 0u;
-      uint4* row = reinterpret_cast<uint4*>(sD + tid * 128);
+      mbar_wait(&d_empty[grp], (k & 1) ^ 1);  // the MMAs of tile i - 2 are done with this buffer
+      uint4* drow = reinterpret_cast<uint4*>(dtile + row * 128);
 #pragma unroll
       for (int c = 0; c < 4; ++c)
-        row[c ^ (tid & 7)] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        drow[c ^ (row & 7)] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d_full[grp]);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {  // the bias gradient sums what the tensor core will see (bf16-rounded)
+      for (int j = 0; j < 16; ++j) {  // the bias gradient sums what the tensor core sees (bf16-rounded)
         if (2 * j < NC) db_acc[2 * j] += bf16lo_to_f32(pk[j]);
         if (2 * j + 1 < NC) db_acc[2 * j + 1] += bf16hi_to_f32(pk[j]);
       }
     }
-    tc_fence_before();     // the logits were read out of TMEM before the next MMA overwrites them
-    fence_proxy_async();   // generic-proxy writes of the dlogits tile -> visible to the tensor core (async proxy)
-    __syncthreads();
-    // ---- dz[128][64] = D[128][32] Wd^T (columns 0..63 of TMEM) and dW[cls][ch] += D^T Z (columns 64..127)
-    if (tid == 0) {
+    {  // bias gradient: per-thread sums over this CTA's tiles -> one column sum per warp
+      float f[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) f[c] = (c < NC) ? db_acc[c] : 0.f;
+      const float colsum = warp_colsum32(f, lane);
+      if (lane < p.C) atomicAdd(&p.dbias[lane], static_cast<double>(colsum));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      ce_local += __shfl_xor_sync(0xffffffffu, ce_local, o);
+      kd_local += __shfl_xor_sync(0xffffffffu, kd_local, o);
+    }
+    if (lane == 0) {
+      atomicAdd(p.loss_acc, static_cast<double>(ce_local));
+      if (KD) atomicAdd(p.loss_acc + 1, static_cast<double>(kd_local));
+    }
+  } else if (warp >= 12) {
+    // ------------------------------------------------ dz store group
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    for (uint32_t i = 0; i < n_local; ++i) {
+      const uint32_t b = i & 1, k = i >> 1;
+      const long long t = blockIdx.x + static_cast<long long>(i) * gridDim.x;
+      const long long pix = t * 128 + row;
+      const bool valid = pix < p.P;
+      mbar_wait(&dz_full[b], k & 1);
       tc_fence_after();
-      const uint32_t daddr = smem_u32(sD);
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-        umma_bf16(tmem_base, umma_smem_desc(daddr + k * 32, 16, 1024), umma_smem_desc(smem_u32(sWd) + k * 32, 16, 1024),
-                  idesc_dz, k != 0 ? 1u : 0u);
-      // MN-major views: A = D^T (M = class; rows 64..127 of M read the first z stage and are never used),
-      // B = Z^T-free view of the same z tile (N = channel), K = the 128 pixels in 8 steps of 16 rows
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_bf16(tmem_base + 64, umma_smem_desc(daddr + k * 2048, kHlTile, 1024),
-                  umma_smem_desc(zaddr + k * 2048, kHlTile, 1024), idesc_dw, (it | k) != 0 ? 1u : 0u);
-      umma_commit(mma_bar);
-    }
-    mbar_wait(mma_bar, ph);
-    ph ^= 1;
-    tc_fence_after();
-    if (tid == 0) {  // z stage s is free again: request the tile after next
-      const long long tn = t + 2ll * gridDim.x;
-      if (tn < tiles) {
-        mbar_arrive_expect_tx(&z_full[s], kHlTile);
-        tma_load_5d(sZ + s * kHlTile, &mapZ, &z_full[s], 0, static_cast<int>(tn * 128), 0, 0, 0);
-      }
-    }
-    // ---- dz row -> bf16 -> global (both 32-column loads in flight before the first use)
-    {
-      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.dz) + (valid ? pix : 0) * 64;
       uint32_t v0[32], v1[32];
-      tmem_ld32(lane_addr, v0);
-      tmem_ld32(lane_addr + 32, v1);
+      tmem_ld32(lane_base + 64 + 64 * b, v0);
+      tmem_ld32(lane_base + 64 + 64 * b + 32, v1);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dz_empty[b]);
       if (valid) {
-        uint4* o = reinterpret_cast<uint4*>(orow);
+        uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dz) + pix * 64);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           o[j] = make_uint4(pack_bf16x2(__uint_as_float(v0[8 * j]), __uint_as_float(v0[8 * j + 1])),
@@ -1793,20 +1869,15 @@ __global__ void __launch_bounds__(kHlThreads, 3)
                                 pack_bf16x2(__uint_as_float(v1[8 * j + 6]), __uint_as_float(v1[8 * j + 7])));
       }
     }
-    tc_fence_before();
-    __syncthreads();  // every thread is done with TMEM columns 0..63 and with the dlogits tile
-  }
-
-  // ---- flush: weight gradient (TMEM lanes = classes), bias gradient, loss
-  if (it > 0) {
-    if (warp == 0) {
+    // the last dz_full also covers the last dW MMA: flush the weight gradient (TMEM lanes 0..31 = classes)
+    if (q == 0 && n_local > 0) {
       tc_fence_after();
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + 64 + half * 32, v);
+        tmem_ld32(tmem_base + 192 + half * 32, v);
         tmem_ld_wait();
-        if (lane < C) {
+        if (lane < p.C) {
           float* o = p.dw + lane * 64 + half * 32;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -1815,25 +1886,10 @@ __global__ void __launch_bounds__(kHlThreads, 3)
         }
       }
     }
-    {  // bias gradient: per-thread sums over this CTA's tiles -> one column sum per warp
-      float f[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) f[c] = (c < NC) ? db_acc[c] : 0.f;
-      const float colsum = warp_colsum32(f, lane);
-      if (lane < C) atomicAdd(&p.dbias[lane], static_cast<double>(colsum));
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-      ce_local += __shfl_xor_sync(0xffffffffu, ce_local, o);
-      kd_local += __shfl_xor_sync(0xffffffffu, kd_local, o);
-    }
-    if (lane == 0) {
-      atomicAdd(p.loss_acc, static_cast<double>(ce_local));
-      if (KD) atomicAdd(p.loss_acc + 1, static_cast<double>(kd_local));
-    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_base, 128);
+  if (warp == 1) tmem_dealloc(tmem_base, kHlTmemCols);
 }
 
 template <int NC, bool KD>
@@ -1845,7 +1901,7 @@ static cudaError_t launch_head_loss_t(const CUtensorMap& z, const CUtensorMap& w
     if (e != cudaSuccess) return e;
   }
   long long grid = (p.P + 127) / 128;
-  if (grid > 3ll * num_sms) grid = 3ll * num_sms;
+  if (grid > num_sms) grid = num_sms;
   launch_k(head_loss_kernel<NC, KD>, dim3(static_cast<unsigned>(grid)), dim3(kHlThreads), kHlSmem, st, z, wf, wd, p);
   return cudaGetLastError();
 }
