@@ -1,7 +1,7 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list of `bench.py --no-graph` per kernel.
 
 usage: python scripts/summarize_launches.py gpurun_out/launches.csv > profiles/<name>.md
-A "step" is delimited by the loss kernel (one launch per training step); the table is the mean over the complete
+A "step" is delimited by the loss kernel (`head_loss_kernel`, one launch per training step); the table is the mean over the complete
 steps in the capture.  ncu serialises launches and runs them cold, so use the SHARES, not the absolute times.
 """
 import csv
@@ -27,7 +27,7 @@ def main(path):
             continue
         rows.append((short(r["Kernel Name"]), float(r["Metric Value"].replace(",", "")) / 1e3, r["Grid Size"],
                      r["Block Size"]))
-    marks = [i for i, r in enumerate(rows) if r[0].startswith("ce_kd_loss")]
+    marks = [i for i, r in enumerate(rows) if r[0].startswith(("ce_kd_loss", "head_loss_kernel"))]
     if len(marks) < 3:
         raise SystemExit("need at least three steps in the capture")
     # a step spans from one loss launch to the next (forward of step k+1 precedes its loss; the sum over a
