@@ -7,10 +7,10 @@ Public surface (mirrors the reference's Python surface for this path):
     metrics                   drop-in for the reference `metrics` module (used half)
     TrainStep                 the fused, CUDA-graph-able step used by bench.py
 """
-from . import _lib, metrics, ops  # noqa: F401
+from . import _lib, metrics, ops, voc  # noqa: F401
 from .loss import CrossEntropyDistillLoss
 from .optim import FusedAdam
 from .step import TrainStep
 from .unet import UNet
 
-__all__ = ["UNet", "CrossEntropyDistillLoss", "FusedAdam", "TrainStep", "metrics", "ops"]
+__all__ = ["UNet", "CrossEntropyDistillLoss", "FusedAdam", "TrainStep", "metrics", "ops", "voc"]

@@ -551,6 +551,20 @@ int clk_head_loss_bwd(const void* z, const void* wf, const void* wd, const float
   return cuda_status(launch_head_loss(mz, mf, md, q, g_num_sms_api, S(st)), "head_loss_bwd");
 }
 
+// ------------------------------------------------------------------ data contract around the step
+int clk_voc_prepare_batch(const void* items, int B, int H, int W, float* x, int64_t* y, int* err_flag,
+                          clk_stream_t st) {
+  if (!items || B < 0 || H <= 0 || W <= 0 || (!x && !y)) return fail(CLK_E_BADARG, "voc_prepare_batch: bad args");
+  return cuda_status(voc_prepare_batch(items, B, H, W, x, reinterpret_cast<long long*>(y), err_flag, S(st)),
+                     "voc_prepare_batch");
+}
+
+int clk_labels_to_rgb(const int64_t* labels, long long n_images, long long hw, double* rgb, clk_stream_t st) {
+  if (!labels || !rgb || n_images < 0 || hw < 0) return fail(CLK_E_BADARG, "labels_to_rgb: bad args");
+  return cuda_status(labels_to_rgb(reinterpret_cast<const long long*>(labels), n_images, hw, rgb, S(st)),
+                     "labels_to_rgb");
+}
+
 // ------------------------------------------------------------------ igemm: plain GEMMs
 static int gemm_fprop_impl(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
                           int out_is_f32, int relu, double* stat_sum, double* stat_sq, const float* bn_scale,

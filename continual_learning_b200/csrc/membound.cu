@@ -1595,4 +1595,94 @@ cudaError_t f64_to_f32_multi(const void* jobs, int njobs, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// Data contract around the step: what datasets/voc.py does per pixel in Python loops.
+// palette of datasets/voc.py:33-54 as 0xRRGGBB; entry 21 = void
+__constant__ unsigned int c_voc_palette[22] = {
+    0x000000, 0x800000, 0x008000, 0x808000, 0x000080, 0x800080, 0x008080, 0x808080, 0x400000, 0xC00000, 0x408000,
+    0xC08000, 0x400080, 0xC00080, 0x408080, 0xC08080, 0x004000, 0x804000, 0x00C000, 0x80C000, 0x004080, 0xE0E0C0};
+
+// One VOC.__getitem__ (datasets/voc.py:127-140) per blockIdx.y after decoding: Pad(10) + CenterCrop((H, W)) as a
+// crop origin (top, left) in source coordinates computed on the host (zero fill outside the source), then
+// ToTensor + Normalize(0.5, 0.5) (main.py:20-21) for the image and to_mask (voc.py:56-72) for the mask.
+// items: int64[8] rows {img u8 [Hs][Ws][3], mask u8 [Hs][Ws][3] or 0, Hs, Ws, top, left, -, -}
+__global__ void __launch_bounds__(256)
+    voc_prepare_kernel(const long long* __restrict__ items, int H, int W, float* __restrict__ x,
+                       long long* __restrict__ y, int* __restrict__ err_flag) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long* J = items + static_cast<long long>(blockIdx.y) * 8;
+  const unsigned char* __restrict__ img = reinterpret_cast<const unsigned char*>(J[0]);
+  const unsigned char* __restrict__ msk = reinterpret_cast<const unsigned char*>(J[1]);
+  const int Hs = static_cast<int>(J[2]), Ws = static_cast<int>(J[3]);
+  const int top = static_cast<int>(J[4]), left = static_cast<int>(J[5]);
+  const long long hw = static_cast<long long>(H) * W;
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < hw;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(q / W), j = static_cast<int>(q % W);
+    const int si = i + top, sj = j + left;
+    const bool inside = si >= 0 && si < Hs && sj >= 0 && sj < Ws;
+    const long long so = (static_cast<long long>(si) * Ws + sj) * 3;
+    if (img != nullptr && x != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = inside ? static_cast<float>(img[so + c]) : 0.f;
+        // ToTensor: v / 255; Normalize: (t - 0.5) / 0.5 — the reference's fp32 operations, no contraction
+        const float t = __fdiv_rn(v, 255.f);
+        x[(static_cast<long long>(blockIdx.y) * 3 + c) * hw + q] = __fdiv_rn(__fsub_rn(t, 0.5f), 0.5f);
+      }
+    }
+    if (msk != nullptr && y != nullptr) {
+      unsigned int key = 0;
+      if (inside) key = (static_cast<unsigned int>(msk[so]) << 16) | (static_cast<unsigned int>(msk[so + 1]) << 8) | msk[so + 2];
+      int label = -1;
+#pragma unroll
+      for (int k = 21; k >= 0; --k)
+        if (key == c_voc_palette[k]) label = k;  // first match wins, as list.index
+      if (label == 21) label = 0;                // void -> background (voc.py:67-68)
+      if (label < 0 && err_flag != nullptr) *err_flag = 1;  // palette.index raises ValueError in the reference
+      y[static_cast<long long>(blockIdx.y) * hw + q] = label;
+    }
+  }
+}
+cudaError_t voc_prepare_batch(const void* items, int B, int H, int W, float* x, long long* y, int* err_flag,
+                              cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  const long long hw = static_cast<long long>(H) * W;
+  int gx = static_cast<int>((hw + 255) / 256);
+  if (gx > 4096) gx = 4096;
+  launch_k(voc_prepare_kernel, dim3(gx, B), dim3(256), 0, st, static_cast<const long long*>(items), H, W, x, y, err_flag);
+  return cudaGetLastError();
+}
+
+// datasets/voc.py:74-89 (to_rgb): class index -> palette colour, float64 [B][3][hw]; indices outside [0, 22) keep
+// their own value in all three channels, exactly as the reference's repeat-then-overwrite does
+__global__ void __launch_bounds__(256)
+    labels_to_rgb_kernel(const long long* __restrict__ labels, long long n_images, long long hw, double* __restrict__ rgb) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long total = n_images * hw;
+  for (long long p = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; p < total;
+       p += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long l = labels[p];
+    const long long b = p / hw, q = p - b * hw;
+    double r = static_cast<double>(l), g = r, bl = r;
+    if (l >= 0 && l < 22) {
+      const unsigned int c = c_voc_palette[l];
+      r = static_cast<double>((c >> 16) & 255u);
+      g = static_cast<double>((c >> 8) & 255u);
+      bl = static_cast<double>(c & 255u);
+    }
+    double* o = rgb + b * 3 * hw + q;
+    o[0] = r;
+    o[hw] = g;
+    o[2 * hw] = bl;
+  }
+}
+cudaError_t labels_to_rgb(const long long* labels, long long n_images, long long hw, double* rgb, cudaStream_t st) {
+  if (n_images * hw <= 0) return cudaSuccess;
+  launch_k(labels_to_rgb_kernel, dim3(grid_for(n_images * hw, 256, 8)), dim3(256), 0, st, labels, n_images, hw, rgb);
+  return cudaGetLastError();
+}
+
 }  // namespace clk

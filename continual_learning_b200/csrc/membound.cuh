@@ -73,4 +73,8 @@ cudaError_t unpack_wgrad_multi(const void* jobs, int njobs, int total_tiles, int
 cudaError_t reduce_partials_multi(const void* jobs, int njobs, int total_blocks, cudaStream_t st);
 cudaError_t f64_to_f32_multi(const void* jobs, int njobs, cudaStream_t st);
 
+cudaError_t voc_prepare_batch(const void* items, int B, int H, int W, float* x, long long* y, int* err_flag,
+                              cudaStream_t st);
+cudaError_t labels_to_rgb(const long long* labels, long long n_images, long long hw, double* rgb, cudaStream_t st);
+
 }  // namespace clk

@@ -21,22 +21,15 @@ from torch.optim.lr_scheduler import LambdaLR
 
 from . import metrics as mt
 from . import parallel
+from . import voc
 from .loss import CrossEntropyDistillLoss
 from .optim import FusedAdam
 from .unet import UNet
 
-# PASCAL-VOC colour map (datasets/voc.py:33-54): 21 classes + void
-_PALETTE = torch.tensor([
-    [0, 0, 0], [128, 0, 0], [0, 128, 0], [128, 128, 0], [0, 0, 128], [128, 0, 128], [0, 128, 128], [128, 128, 128],
-    [64, 0, 0], [192, 0, 0], [64, 128, 0], [192, 128, 0], [64, 0, 128], [192, 0, 128], [64, 128, 128],
-    [192, 128, 128], [0, 64, 0], [128, 64, 0], [0, 192, 0], [128, 192, 0], [0, 64, 128], [224, 224, 192]],
-    dtype=torch.float32) / 255.0
-
-
 def to_rgb(labels):
-    """label map [B,H,W] -> colour image [B,3,H,W] in [0,1] via a palette lookup (datasets/voc.py:74-89)."""
-    pal = _PALETTE.to(labels.device)
-    return pal[labels.clamp(0, pal.shape[0] - 1)].permute(0, 3, 1, 2).contiguous()
+    """label map [B,H,W] -> colour image [B,3,H,W] in [0,1]: the device form of datasets/voc.py:74-89
+    (`voc.to_rgb`, float64 0..224 like the reference's) scaled for `save_image`."""
+    return (voc.to_rgb(labels.contiguous()) / 255.0).float()
 
 
 class Trainer:

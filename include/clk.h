@@ -202,6 +202,20 @@ int clk_adam_multi_tensor(const void* tensors, const void* blocks, int nblocks, 
                           float b1, float b2, float eps, float bc1, float bc2_sqrt, float gscale,
                           const float* hyper_dev, clk_stream_t st);
 
+/* ---- data contract on either side of the step ----
+ * One VOC.__getitem__ per sample after image decoding (datasets/voc.py:127-140 with the transform of main.py:17-23):
+ * Pad(10) + CenterCrop((H, W)) expressed as the crop origin (top, left) in source coordinates (zero fill outside the
+ * source; the host computes it with torchvision's rounding), ToTensor + Normalize(0.5, 0.5) on the image and to_mask
+ * (datasets/voc.py:56-72: palette RGB -> class index, void -> 0) on the mask.
+ * items: device int64[B][8] rows {img u8 [Hs][Ws][3], mask u8 [Hs][Ws][3], Hs, Ws, top, left, 0, 0} (either pointer
+ * may be 0).  x: f32 [B][3][H][W] bit-equal to the reference's; y: int64 [B][H][W]; a colour that is not in the
+ * palette (the reference raises ValueError) writes -1 and sets *err_flag. */
+int clk_voc_prepare_batch(const void* items, int B, int H, int W, float* x, int64_t* y, int* err_flag,
+                          clk_stream_t st);
+/* datasets/voc.py:74-89 (to_rgb, used by the sample dump trainer.py:193-194): labels int64 [B][hw] ->
+ * f64 [B][3][hw] palette colours; indices outside [0, 22) keep their value in all three channels. */
+int clk_labels_to_rgb(const int64_t* labels, long long n_images, long long hw, double* rgb, clk_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif
