@@ -355,7 +355,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--image", type=int, default=256, help="square image size (default = BASELINE config 2; 512 = "
+                    "the per-GPU shape of config 4)")
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU")
     args = ap.parse_args()
+    global BATCH, H, W, WORKLOAD, GFLOP_PER_IMG_TRAIN
+    if args.image != 256 or args.batch != 16:
+        GFLOP_PER_IMG_TRAIN *= (args.image * args.image) / float(H * W)
+        BATCH, H, W = args.batch, args.image, args.image
+        WORKLOAD = f"unet21_{H}x{W}_b{BATCH}_train_single_task"
+        args.no_cpu_baseline = True  # the CPU sample is defined on the default workload only
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -37,19 +37,10 @@ def time_cfg(flags, tune, steps=40):
 if __name__ == "__main__":
     base = dict(use_side_stream=True, fuse_bn=False, side_pack=True)
     nos = dict(use_side_stream=False, side_pack=False)
-    variants = [("default", {}, {}), ("pdl off", {}, {"pdl": 0}),
-                ("pdl, tensor trigger at start", {}, {"pdl": 1, "pdl_tensor_trigger": 0}),
-                ("pdl, trigger after last load", {}, {"pdl_tensor_trigger": 1}),
-                ("pdl, trigger at exit", {}, {"pdl_tensor_trigger": 2}),
-                ("pdl off", {}, {"pdl": 0}),
-                ("pdl, tensor trigger at start", {}, {"pdl": 1, "pdl_tensor_trigger": 0}),
-                ("pdl, trigger after last load", {}, {"pdl_tensor_trigger": 1}),
-                ("pdl, trigger at exit", {}, {"pdl_tensor_trigger": 2}),
-                ("1 stream, pdl off", nos, {"pdl": 0}),
-                ("1 stream, trigger at start", nos, {"pdl": 1, "pdl_tensor_trigger": 0}),
-                ("1 stream, trigger after last load", nos, {"pdl_tensor_trigger": 1}),
-                ("1 stream, trigger at exit", nos, {"pdl_tensor_trigger": 2}),
-                ("default", {}, {"pdl_tensor_trigger": 1})]
+    nos = dict(use_side_stream=False, side_pack=False)
+    nos = dict(use_side_stream=False, side_pack=False)
+    variants = [("default", {}, {}), ("pdl off", {}, {"pdl": 0}), ("default", {}, {"pdl": 1}),
+                ("one stream", nos, {}), ("default", {}, {})]
     if "--all" in sys.argv:
         sys.argv.remove("--all")
         variants += [("fuse_bn", dict(fuse_bn=True), {"pdl": 1}), ("no side_pack", dict(side_pack=False), {}),
