@@ -178,7 +178,12 @@ def run_b200(args):
     if world > 1:
         names = [k for k, _ in model.named_parameters()]
         comm = parallel.GradAllReduce([p.numel() for p in model.parameters()], names)
-    ts = clk.TrainStep(model, opt, use_graph=(world == 1 and not args.no_graph), comm=comm)
+    old_model = None
+    if args.continual:  # BASELINE config 3: + frozen previous-task network UNet(16) in eval mode, T = 2, lambda = 1
+        old_model = clk.UNet(16).to(dev)
+        old_model.eval()
+    ts = clk.TrainStep(model, opt, old_model=old_model, T=2.0, lam=1.0, use_graph=(world == 1 and not args.no_graph),
+                       comm=comm)
 
     # synthetic VOC-shaped data: a few distinct batches per rank, resident in HBM for `value`,
     # in pinned host memory for `e2e`
@@ -251,7 +256,7 @@ def run_b200(args):
     d2h = 8
 
     # ---- per-kernel timing of one eager step (CUDA events around every clk_* launch) -> roofline
-    ts_prof = clk.TrainStep(model, opt, use_graph=False, comm=comm)
+    ts_prof = clk.TrainStep(model, opt, old_model=old_model, T=2.0, lam=1.0, use_graph=False, comm=comm)
     ts_prof.step_count = ts.step_count
     model.engine.use_side_stream = False  # serialise the weight-gradient stream: one kernel at a time under the events
     ts_prof.step(*devb[0])
@@ -358,12 +363,14 @@ def main():
     ap.add_argument("--image", type=int, default=256, help="square image size (default = BASELINE config 2; 512 = "
                     "the per-GPU shape of config 4)")
     ap.add_argument("--batch", type=int, default=16, help="images per GPU")
+    ap.add_argument("--continual", action="store_true", help="BASELINE config 3: the continual step (distillation "
+                    "against a frozen UNet(16)); images/s of that step")
     args = ap.parse_args()
     global BATCH, H, W, WORKLOAD, GFLOP_PER_IMG_TRAIN
-    if args.image != 256 or args.batch != 16:
+    if args.image != 256 or args.batch != 16 or args.continual:
         GFLOP_PER_IMG_TRAIN *= (args.image * args.image) / float(H * W)
         BATCH, H, W = args.batch, args.image, args.image
-        WORKLOAD = f"unet21_{H}x{W}_b{BATCH}_train_single_task"
+        WORKLOAD = f"unet21_{H}x{W}_b{BATCH}_train_" + ("continual_kd16" if args.continual else "single_task")
         args.no_cpu_baseline = True  # the CPU sample is defined on the default workload only
     if args.impl == "reference":
         run_reference(args)
