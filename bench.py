@@ -114,13 +114,20 @@ def measured_peaks():
 
 
 # ---------------------------------------------------------------------------------------------
-def cpu_step_throughput(steps, warmup, batch, threads=None):
-    """the reference training step (trainer.py:172-176) through the CPU oracle port, fp32, all host threads."""
+def cpu_step_throughput(steps, warmup, batch, threads=None, budget_s=150.0):
+    """the reference training step (trainer.py:172-176) through the CPU oracle port, fp32, all host threads
+    (torchrun exports OMP_NUM_THREADS=1: overridden here, rank 0 is the only rank doing CPU work).  Stops early when
+    the time budget is used up, so `--steps 100` still ends within a few minutes on a slow host."""
     from oracle import step_ref
     from oracle.data import uniform_batch
     from oracle.unet_ref import make_state_dict, param_names
-    if threads:
-        torch.set_num_threads(threads)
+    if threads is None:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(max(1, threads))
+    t_begin = time.perf_counter()
     sd = make_state_dict(0, NUM_CLASSES)
     opt = step_ref.AdamRef(param_names(sd), lr=1e-4, betas=(0.5, 0.99))
     x, y = uniform_batch(1, batch, H, W, NUM_CLASSES)
@@ -132,7 +139,9 @@ def cpu_step_throughput(steps, warmup, batch, threads=None):
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
-    return batch / statistics.median(times), statistics.median(times), torch.get_num_threads()
+            if time.perf_counter() - t_begin > budget_s:
+                break
+    return batch / statistics.median(times), statistics.median(times), torch.get_num_threads(), len(times)
 
 
 def run_reference(args):
@@ -140,9 +149,9 @@ def run_reference(args):
     if rank != 0:
         return
     sample_batch = 2
-    val, sec, cores = cpu_step_throughput(args.steps, args.warmup, sample_batch)
+    val, sec, cores, ran = cpu_step_throughput(max(1, args.steps), args.warmup, sample_batch)
     sample = (f"oracle port of trainer.py:172-176 (fp32 CPU), batch {sample_batch} of the {BATCH}-image 256x256 step, "
-              f"{args.steps} steps after {args.warmup} warm-up, median {sec:.3f} s/step")
+              f"{ran} of {args.steps} steps timed after {args.warmup} warm-up (150 s budget), median {sec:.3f} s/step")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -292,7 +301,7 @@ def run_b200(args):
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = cpu_step_throughput(steps=4, warmup=1, batch=2)
+        v, sec, cores, _ = cpu_step_throughput(steps=4, warmup=1, batch=2)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"oracle port of trainer.py:172-176, fp32, batch 2 x 256x256 (BASELINE config 1 shape), 4 steps after 1 warm-up, median {sec:.3f} s/step"}
     line = {
