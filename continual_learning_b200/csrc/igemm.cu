@@ -1048,7 +1048,7 @@ __global__ void __launch_bounds__(kC3Threads, 1)
       mbar_wait(&acc_full[acc], pacc);
       tc_fence_after();
 #pragma unroll 1
-      for (int chunk = 0; chunk < (p.relu == 77 ? 0 : BN / 32); ++chunk) {  // relu == 77: debug, main loop only
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 2 * BN + j * BN + chunk * 32, v);
         tmem_ld_wait();

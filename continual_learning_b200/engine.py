@@ -366,10 +366,6 @@ class UNetEngine:
             dpre = ops.bn_relu_bwd_apply(dz, u.y, ka, kb, kc, u.dbias)
         else:
             dpre = self._bn_bwd_fused(u, dz, n * h * w)
-        if False:
-            dpre = ops.bn_relu_bwd_apply_fused(dz, u.y, u.s1, u.s2, bn.weight.detach(), u.vec[0], u.vec[1],
-                                           self.gview[bn.weight], self.gview[bn.bias], u.dbias, n * h * w,
-                                           training=self.training_fwd)
         # the weight gradient only feeds the optimiser: run it on the side stream so that it overlaps the dgrad of
         # this layer and the (HBM-bound) BatchNorm backward of the next one
         with self._fork(dpre):
