@@ -26,6 +26,7 @@ int g_conv3_v2 = 4;          // conv3x3 fprop/dgrad kernel: 0 generic, 1 hybrid,
 int g_conv3_pair = 1;        // CTA-pair kernel (cta_group::2, BN = 256) whenever the N extent is a multiple of 256
 int g_conv3_min_hw = 2048;  // halo kernel for images with at least this many pixels; smaller maps use the generic kernel (BN up to 256)
 int g_num_sms_api = 148;
+int g_convT_wide = 1;         // ConvTranspose2d forward: 256-column N tiles across quadrants
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -234,6 +235,7 @@ int clk_set_tuning(const char* key, int value) {
   else if (strcmp(key, "conv3_min_hw") == 0) g_conv3_min_hw = value;
   else if (strcmp(key, "conv3_pair") == 0) g_conv3_pair = value;
   else if (strcmp(key, "pdl") == 0) g_pdl = value ? 1 : 0;
+  else if (strcmp(key, "convT_wide") == 0) g_convT_wide = value ? 1 : 0;
   else if (strcmp(key, "pdl_tensor_trigger") == 0) return cuda_status(igemm_set_pdl_mode(value), "pdl_tensor_trigger");
   else return fail(CLK_E_BADARG, "unknown tuning key %s", key);
   return CLK_OK;
@@ -660,7 +662,9 @@ int clk_convT2x2_fprop(const void* x, const void* w, const float* bias, void* y,
   p.dst0 = y;
   p.ldc0 = Cout;
   p.bias = bias;
-  const int BN = pick_bn(Cout);
+  // N tiles of 256 columns span several quadrants when Cout < 256: the input tile is read once per 256 output
+  // columns instead of once per quadrant (the epilogue picks the destination pixel per 32-column chunk)
+  const int BN = g_convT_wide ? 256 : pick_bn(Cout);
   CUtensorMap a0, b;
   CHECK_RC(map_linear(&a0, x, P, Cin, 128));
   CHECK_RC(map_weights(&b, w, 1, 4 * Cout, Cin, BN));

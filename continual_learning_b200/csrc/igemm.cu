@@ -258,6 +258,10 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
         colbase = n0 - p.split_c;
       }
       OutT* drow = dst + (valid ? pix : 0) * ld + colbase;
+      // ConvTranspose2d pixel shuffle with an N tile that spans several quadrants (BN > cout_q): the destination
+      // pixel is chosen per 32-column chunk (cout_q is a multiple of 64, a chunk never straddles two quadrants)
+      const bool shuffle_chunks = p.shuffle && BN > p.cout_q;
+      const long long pix_q0 = (static_cast<long long>(pn) * (2 * p.g.H) + 2 * ph_) * (2 * p.g.W) + 2 * pw;
 
       mbar_wait(&acc_full[acc], pacc);
       tc_fence_after();
@@ -279,7 +283,13 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
           if (valid && (n0 + chunk * 32) < p.n_store) {
-            uint4* o = reinterpret_cast<uint4*>(drow + chunk * 32);
+            OutT* crow = drow + chunk * 32;
+            if (shuffle_chunks) {
+              const int gcol = n0 + chunk * 32;
+              const int qd = gcol / p.cout_q;
+              crow = dst + (pix_q0 + (qd >> 1) * (2 * p.g.W) + (qd & 1)) * ld + (gcol - qd * p.cout_q);
+            }
+            uint4* o = reinterpret_cast<uint4*>(crow);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               o[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
