@@ -44,6 +44,7 @@ SIGNATURES = {
     "clk_gemm_fprop": [p, i, p, p, p, i, i, i, i, p, p, ll, i, p],
     "clk_gemm_fprop_eval": [p, i, p, p, p, i, i, i, p, p, ll, i, p],
     "clk_gemm_wgrad": [p, i, p, i, p, i, i, ll, p],
+    "clk_head_argmax_confusion": [p, p, p, p, ll, i, i, i, p, p, p, p],
     "clk_head_loss_bwd": [p, p, p, p, p, p, ll, i, i, i, f, f, f, p, p, p, p, p, p],
     "clk_convT2x2_fprop": [p, p, p, p, i, i, i, i, i, p],
     "clk_convT2x2_dgrad": [p, p, p, i, i, i, i, i, p],

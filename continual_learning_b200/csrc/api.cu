@@ -567,6 +567,26 @@ int clk_labels_to_rgb(const int64_t* labels, long long n_images, long long hw, d
                      "labels_to_rgb");
 }
 
+int clk_head_argmax_confusion(const void* z, const void* wf, const float* bias, const int64_t* labels, long long P,
+                              int Cin, int C, int nc, int64_t* pred_out, int64_t* conf, int64_t* correct,
+                              clk_stream_t st) {
+  if (!z || !wf || !labels || P <= 0) return fail(CLK_E_BADARG, "head_argmax_confusion: bad args");
+  if (Cin != 64 || C < 1 || C > 32 || nc < C || nc > 64)
+    return fail(CLK_E_UNSUPPORTED_SHAPE, "head_argmax_confusion: needs Cin == 64, 1 <= C <= 32, C <= nc <= 64 (Cin=%d C=%d nc=%d)",
+                Cin, C, nc);
+  if (P > 2000000000LL) return fail(CLK_E_UNSUPPORTED_SHAPE, "head_argmax_confusion: P too large");
+  HeadArgmaxParams q;
+  memset(&q, 0, sizeof(q));
+  q.P = P; q.C = C; q.nc = nc; q.bias = bias; q.labels = reinterpret_cast<const long long*>(labels);
+  q.pred_out = reinterpret_cast<long long*>(pred_out);
+  q.conf = reinterpret_cast<unsigned long long*>(conf);
+  q.correct = reinterpret_cast<unsigned long long*>(correct);
+  CUtensorMap mz, mf;
+  CHECK_RC(map_linear(&mz, z, P, 64, 128));
+  CHECK_RC(map_weights(&mf, wf, 1, 32, 64, 32));
+  return cuda_status(launch_head_argmax(mz, mf, q, g_num_sms_api, S(st)), "head_argmax_confusion");
+}
+
 // ------------------------------------------------------------------ igemm: plain GEMMs
 static int gemm_fprop_impl(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
                           int out_is_f32, int relu, double* stat_sum, double* stat_sq, const float* bn_scale,

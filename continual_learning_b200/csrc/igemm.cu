@@ -1927,4 +1927,145 @@ cudaError_t launch_head_loss(const CUtensorMap& z, const CUtensorMap& wf, const 
             : launch_head_loss_t<32, false>(z, wf, wd, p, num_sms, st);
 }
 
+// ------------------------------------------------------------------------------------------
+// HEAD + ARGMAX + CONFUSION MATRIX in one kernel: the statistics / validation path of the reference
+// (models/unet.py:72 -> argmax(softmax(out), 1), .eq(labels).sum(), metrics._fast_conf_matrix: trainer.py:183-184,
+// 279, metrics.py:32-38).  The logits stay in tensor memory: z is read once, nothing but the optional prediction map
+// is written.  128 threads per CTA (thread = pixel = TMEM lane), two logits buffers so that the MMA of tile i + 1
+// runs under the arg-max of tile i, several CTAs per SM; per-warp shared-memory histograms, int64 global bins.
+// Same tie / NaN rule as argmax_confusion_kernel (first maximum wins, a NaN beats every number).
+constexpr int kHaThreads = 128;
+__global__ void __launch_bounds__(kHaThreads, 4)
+    head_argmax_kernel(const __grid_constant__ CUtensorMap mapZ, const __grid_constant__ CUtensorMap mapWf,
+                       const __grid_constant__ HeadArgmaxParams p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sZ = smem;                       // two z stages
+  uint8_t* sWf = sZ + 2 * kHlTile;          // [32 cls][64 ch]
+  uint64_t* z_full = reinterpret_cast<uint64_t*>(sWf + 32 * 128);
+  uint64_t* w_full = z_full + 2;
+  uint64_t* lg_full = w_full + 1;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lg_full + 2);
+  unsigned int* hist = reinterpret_cast<unsigned int*>(tmem_slot + 4);  // [4 warps][nc * nc]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nbins = p.nc * p.nc;
+  const long long tiles = (p.P + 127) / 128;
+  const uint32_t n_local = blockIdx.x < tiles ? static_cast<uint32_t>((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+  if (tid == 0) {
+    mbar_init(&z_full[0], 1);
+    mbar_init(&z_full[1], 1);
+    mbar_init(w_full, 1);
+    mbar_init(&lg_full[0], 1);
+    mbar_init(&lg_full[1], 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&mapZ);
+    tma_prefetch_desc(&mapWf);
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  if (p.conf != nullptr)
+    for (int i = tid; i < 4 * nbins; i += kHaThreads) hist[i] = 0u;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 32, 0, 0);
+  auto tile_of = [&](uint32_t i) { return blockIdx.x + static_cast<long long>(i) * gridDim.x; };
+  auto issue_logits = [&](uint32_t i) {  // thread 0: logits[128][32] of local tile i into buffer i & 1
+    const uint32_t s = i & 1;
+    mbar_wait(&z_full[s], (i >> 1) & 1);
+    tc_fence_after();
+    const uint32_t zaddr = smem_u32(sZ + s * kHlTile);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem_base + 32 * s, umma_smem_desc(zaddr + k * 32, 16, 1024),
+                umma_smem_desc(smem_u32(sWf) + k * 32, 16, 1024), idesc, k != 0 ? 1u : 0u);
+    umma_commit(&lg_full[s]);
+  };
+  if (tid == 0 && n_local > 0) {
+    mbar_arrive_expect_tx(w_full, 32 * 128);
+    tma_load_3d(sWf, &mapWf, w_full, 0, 0, 0);
+    for (uint32_t i = 0; i < 2 && i < n_local; ++i) {
+      mbar_arrive_expect_tx(&z_full[i], kHlTile);
+      tma_load_5d(sZ + i * kHlTile, &mapZ, &z_full[i], 0, static_cast<int>(tile_of(i) * 128), 0, 0, 0);
+    }
+    mbar_wait(w_full, 0);
+    issue_logits(0);
+  }
+
+  float bias_r[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) bias_r[c] = (c < p.C && p.bias != nullptr) ? p.bias[c] : 0.f;
+  unsigned int* mine = hist + warp * nbins;
+  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  unsigned int ok = 0;
+  for (uint32_t i = 0; i < n_local; ++i) {
+    const uint32_t s = i & 1;
+    if (tid == 0 && i + 1 < n_local) issue_logits(i + 1);  // its buffer was drained before the barrier below (tile i - 1)
+    const long long pix = tile_of(i) * 128 + tid;
+    const bool valid = pix < p.P;
+    const long long t = valid ? p.labels[pix] : -1;
+    mbar_wait(&lg_full[s], (i >> 1) & 1);
+    tc_fence_after();
+    uint32_t v[32];
+    tmem_ld32(lane_addr + 32 * s, v);
+    tmem_ld_wait();
+    float best = __uint_as_float(v[0]) + bias_r[0];
+    int bi = 0;
+#pragma unroll
+    for (int c = 1; c < 32; ++c) {
+      const float x = __uint_as_float(v[c]) + bias_r[c];
+      if (c < p.C && (x > best || (x != x && best == best))) {
+        best = x;
+        bi = c;
+      }
+    }
+    if (valid) {
+      if (p.pred_out != nullptr) p.pred_out[pix] = bi;
+      if (t == bi) ++ok;
+      if (p.conf != nullptr && t >= 0 && t < p.nc) atomicAdd(mine + t * p.nc + bi, 1u);
+    }
+    tc_fence_before();
+    __syncthreads();  // logits buffer s and (its MMA being complete) z stage s are free
+    if (tid == 0 && i + 2 < n_local) {
+      mbar_arrive_expect_tx(&z_full[s], kHlTile);
+      tma_load_5d(sZ + s * kHlTile, &mapZ, &z_full[s], 0, static_cast<int>(tile_of(i + 2) * 128), 0, 0, 0);
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) ok += __shfl_xor_sync(0xffffffffu, ok, o);
+  if (lane == 0 && ok && p.correct != nullptr) atomicAdd(p.correct, static_cast<unsigned long long>(ok));
+  __syncthreads();
+  if (p.conf != nullptr) {
+    for (int b = tid; b < nbins; b += kHaThreads) {
+      unsigned long long sum = 0;
+      for (int w = 0; w < 4; ++w) sum += hist[w * nbins + b];
+      if (sum) atomicAdd(p.conf + b, sum);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 64);
+}
+
+cudaError_t launch_head_argmax(const CUtensorMap& z, const CUtensorMap& wf, const HeadArgmaxParams& p, int num_sms,
+                               cudaStream_t st) {
+  const int smem = 2 * kHlTile + 32 * 128 + 5 * 8 + 16 + 4 * p.nc * p.nc * 4 + 1024;
+  if (smem > 100 * 1024) return cudaErrorInvalidValue;
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
+    cudaError_t e = cudaFuncSetAttribute(head_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return e;
+  }
+  long long grid = (p.P + 127) / 128;
+  if (grid > 4ll * num_sms) grid = 4ll * num_sms;
+  launch_k(head_argmax_kernel, dim3(static_cast<unsigned>(grid)), dim3(kHaThreads), smem, st, z, wf, p);
+  return cudaGetLastError();
+}
+
 }  // namespace clk

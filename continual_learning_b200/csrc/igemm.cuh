@@ -139,4 +139,18 @@ struct HeadLossParams {
 cudaError_t launch_head_loss(const CUtensorMap& z, const CUtensorMap& wf, const CUtensorMap& wd, const HeadLossParams& p,
                              int num_sms, cudaStream_t st);
 
+// fused 1x1 head + arg-max + confusion matrix (statistics / validation path), see head_argmax_kernel
+struct HeadArgmaxParams {
+  long long P;
+  int C, nc;
+  const float* bias;
+  const long long* labels;
+  long long* pred_out;             // [P] or null
+  unsigned long long* conf;        // [nc * nc] accumulated, or null
+  unsigned long long* correct;     // accumulated count of pred == label, or null
+};
+// z box {64, 128}; wf box {64, 32, 1}
+cudaError_t launch_head_argmax(const CUtensorMap& z, const CUtensorMap& wf, const HeadArgmaxParams& p, int num_sms,
+                               cudaStream_t st);
+
 }  // namespace clk

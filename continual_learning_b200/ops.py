@@ -351,6 +351,22 @@ def head_loss_bwd(z, wf, wd, bias, labels, num_classes, old_logits=None, T=2.0, 
     return loss_acc, dz, dw, dbias
 
 
+def head_argmax_confusion(z, wf, bias, labels, num_classes, nc=None, want_pred=False, conf=None, correct=None):
+    """1x1 head + argmax + correct count + confusion matrix in one launch (the logits never leave tensor memory).
+    z bf16 [..., 64]; returns (pred int64 or None, conf int64 [nc*nc] or None, correct int64 [1])."""
+    _dev(z)
+    cin = z.shape[-1]
+    p = z.numel() // cin
+    pred = torch.empty(z.shape[:-1], device=z.device, dtype=torch.int64) if want_pred else None
+    if nc is not None and conf is None:
+        conf = torch.zeros(nc * nc, device=z.device, dtype=torch.int64)
+    if correct is None:
+        correct = torch.zeros(1, device=z.device, dtype=torch.int64)
+    _lib.call("clk_head_argmax_confusion", z, wf, bias, labels, p, cin, num_classes,
+              nc if nc is not None else num_classes, pred, conf if nc is not None else None, correct)
+    return pred, conf, correct
+
+
 def confusion_matrix(target, pred, nc, conf=None, err_flag=None):
     if conf is None:
         conf = torch.zeros(nc * nc, device=target.device, dtype=torch.int64)

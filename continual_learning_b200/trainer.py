@@ -201,9 +201,8 @@ class Trainer:
                 if self.world > 1:
                     images = parallel.shard_batch(images, self.rank, self.world)
                     labels = parallel.shard_batch(labels, self.rank, self.world)
-                outputs = self.model(images)
-                _, c, _ = mt.predict_and_count(outputs, labels, None)
-                correct += c
+                # forward + head + argmax + correct count in inference mode, logits never materialised
+                self.model.evaluate_batch(images, labels, correct=correct)
                 total += labels.nelement()
         tot = torch.tensor([total], device=self.device, dtype=torch.int64)
         _, both = parallel.all_reduce_confusion(correct.new_zeros(0), torch.cat([correct, tot]))

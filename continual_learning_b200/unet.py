@@ -8,6 +8,7 @@ parameters and buffers; they are never called.  CUDA (sm_100a) only — no CPU f
 import torch
 import torch.nn as nn
 
+from . import ops
 from .engine import UNetEngine
 
 
@@ -96,6 +97,22 @@ class UNet(nn.Module):
             return _UNetFn.apply(x, eng, self.training, *self.parameters())
         logits = eng.forward(x, training=self.training, save_for_backward=False)
         out = logits.permute(0, 3, 1, 2)
+        return out
+
+    @torch.no_grad()
+    def evaluate_batch(self, x, labels, nc=None, conf=None, correct=None, want_pred=False):
+        """statistics / validation step in inference mode (trainer.py:183-189, 271-280): forward with BatchNorm
+        folded into the conv epilogues, then the 1x1 head, argmax, the correct-pixel count and the confusion matrix
+        (rows = target, `nc` classes) in ONE kernel — the logits are never written.  Accumulates into `conf`
+        (int64 [nc*nc]) and `correct` (int64 [1]) when given.  Returns (pred int64 [B,H,W] or None, conf, correct).
+        Uses the current mode's statistics: call `.eval()` first for the reference's test() semantics."""
+        if not x.is_cuda:
+            raise RuntimeError("continual_learning_b200.UNet needs CUDA tensors (sm_100a); there is no CPU fallback")
+        eng = self.engine
+        z = eng.forward(x, training=self.training, save_for_backward=False, head=False)
+        out = ops.head_argmax_confusion(z, eng.hwf, eng.head.bias.detach(), labels.contiguous(), self.num_classes, nc=nc,
+                                        want_pred=want_pred, conf=conf, correct=correct)
+        eng.release()
         return out
 
     def logits_nhwc(self):

@@ -121,6 +121,14 @@ int clk_head_loss_bwd(const void* z, const void* wf, const void* wd, const float
                       const float* old_logits, long long P, int Cin, int C, int Cold, float T, float lambda,
                       float gscale, void* dz, float* dw, double* dbias, double* loss_acc, int* err_flag,
                       clk_stream_t st);
+/* Statistics / validation path in ONE launch: the 1x1 head (models/unet.py:72), argmax over classes
+ * (trainer.py:183,279), the correct-pixel count (trainer.py:184) and metrics._fast_conf_matrix (metrics.py:32-38)
+ * without materialising the logits.  z bf16 [P][64]; wf bf16 [32][64]; bias f32[C] or NULL; labels int64[P];
+ * pred_out int64[P] or NULL; conf int64[nc*nc] += (rows = target, targets outside [0, nc) skipped) or NULL;
+ * correct int64[1] += or NULL.  Same results as clk_gemm_fprop (fp32 logits) + clk_argmax_confusion. */
+int clk_head_argmax_confusion(const void* z, const void* wf, const float* bias, const int64_t* labels, long long P,
+                              int Cin, int C, int nc, int64_t* pred_out, int64_t* conf, int64_t* correct,
+                              clk_stream_t st);
 /* out fp32 [ld_u][ld_t] += u[P][CU]^T * t[P][CT]  (weight gradient of the GEMMs above) */
 int clk_gemm_wgrad(const void* u, int CU, const void* t, int CT, float* out, int ld_u, int ld_t,
                    long long P, clk_stream_t st);

@@ -23,9 +23,12 @@ def main():
     y = torch.randint(0, 21, (b, 256, 256), generator=g).cuda()
     conf = torch.zeros(21 * 21, device="cuda", dtype=torch.int64)
     correct = torch.zeros(1, device="cuda", dtype=torch.int64)
-    for fused in (True, False):
+    for mode in ("one head kernel", "BN folded", "separate passes"):
         def fwd():
-            logits = m.engine.forward(x, training=False, save_for_backward=not fused)
+            if mode == "one head kernel":
+                m.evaluate_batch(x, y, nc=21, conf=conf, correct=correct)
+                return
+            logits = m.engine.forward(x, training=False, save_for_backward=mode != "BN folded")
             ops.argmax_confusion(logits, y, 21, conf=conf, correct=correct)
             m.engine.release()
         with torch.no_grad():
@@ -39,8 +42,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
-        print(f"eval forward + confusion, batch {b}, BN {'fused in conv epilogue' if fused else 'separate passes'}: "
-              f"{ms:.3f} ms/batch = {b / ms * 1e3:.0f} img/s")
+        print(f"eval forward + confusion, batch {b}, {mode}: {ms:.3f} ms/batch = {b / ms * 1e3:.0f} img/s")
 
 
 if __name__ == "__main__":

@@ -245,6 +245,15 @@ def test_validation_sweep_confusion_matrix_exact(clk):
             want += metrics_ref.conf_matrix_int(y.numpy(), pred.cpu().numpy(), 21)
             n_ok += int((pred.cpu() == y).sum())
     assert np.array_equal(conf.view(21, 21).cpu().numpy(), want) and int(correct) == n_ok
+    # the one-kernel form (head + argmax + counts, logits never written) gives the same predictions and counts
+    conf2 = torch.zeros(21 * 21, device="cuda", dtype=torch.int64)
+    correct2 = torch.zeros(1, device="cuda", dtype=torch.int64)
+    for i in range(3):
+        x, y = uniform_batch(50 + i, 2, 64, 64)
+        pred2, _, _ = m.evaluate_batch(x.cuda(), y.cuda(), nc=21, conf=conf2, correct=correct2, want_pred=True)
+        with torch.no_grad():
+            assert torch.equal(pred2, m(x.cuda()).argmax(1))
+    assert torch.equal(conf2, conf) and torch.equal(correct2, correct)
 
 
 def test_metrics_drop_in_on_reference_golden(clk, golden_dir):

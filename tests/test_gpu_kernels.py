@@ -445,3 +445,24 @@ def test_unsupported_shapes_are_rejected_not_miscomputed(ops):
         ops.conv3x3_fprop(x, None, w, None)
     with pytest.raises(ClkError, match="UNSUPPORTED_SHAPE"):
         ops.im2col_stem(torch.zeros(1, 8, 4, 4, device="cuda"))
+
+
+@pytest.mark.parametrize("P,c,nc", [(1000, 21, 22), (128 * 300 + 5, 21, 21), (513, 2, 2), (64, 7, 9)])
+def test_fused_head_argmax_confusion_equals_the_separate_ops(ops, P, c, nc):
+    """clk_head_argmax_confusion == 1x1 head GEMM (fp32 logits) -> clk_argmax_confusion, bit for bit (same MMA, same
+    tie rule), and the counts equal numpy's on those predictions."""
+    g = gen(P + c)
+    z = bfr(rnd(g, P, 64)).to(torch.bfloat16).cuda()
+    w = bfr(rnd(g, c, 64, scale=0.2))
+    b = rnd(g, c).cuda()
+    y = torch.randint(0, nc, (P,), generator=g).cuda()
+    wf, _ = ops.pack_head(w.view(c, 64, 1, 1).cuda())
+    logits = ops.gemm_fprop(z, wf, b, c, out_f32=True)
+    pred_ref, conf_ref, ok_ref = ops.argmax_confusion(logits, y, nc, want_pred=True)
+    pred, conf, ok = ops.head_argmax_confusion(z, wf, b, y, c, nc=nc, want_pred=True)
+    assert torch.equal(pred, pred_ref) and torch.equal(conf, conf_ref) and torch.equal(ok, ok_ref)
+    want = np.bincount((nc * y.cpu().numpy() + pred.cpu().numpy()), minlength=nc * nc)
+    assert np.array_equal(conf.cpu().numpy(), want)
+    # accumulating form, no prediction map
+    _, conf2, ok2 = ops.head_argmax_confusion(z, wf, b, y, c, nc=nc, conf=conf.clone(), correct=ok.clone())
+    assert torch.equal(conf2, 2 * conf_ref) and torch.equal(ok2, 2 * ok_ref)
