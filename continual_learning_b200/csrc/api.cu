@@ -20,6 +20,7 @@ namespace {
 thread_local char g_err[512] = "";
 int g_fprop_bn = 0;
 int g_wgrad_ksplit = 0;
+int g_wgrad_ctas = 0;         // generic wgrad: total CTAs aimed at by the split-K heuristic (0 = 2 per SM)
 int g_wgrad_bn = 64;
 int g_wgrad_v2 = 2;          // conv3x3 wgrad: 0 generic, 1 halo (1 CTA), 2 CTA-pair halo where Cout % 128 == 0 (default)
 int g_conv3_v2 = 4;          // conv3x3 fprop/dgrad kernel: 0 generic, 1 hybrid, 2 halo (1 CTA), 4 CTA-pair halo (default)
@@ -188,7 +189,7 @@ int pick_bn(int ncols) {
 }
 int pick_ksplit(int base_ctas, int tiles_total) {
   if (g_wgrad_ksplit > 0) return g_wgrad_ksplit < tiles_total ? g_wgrad_ksplit : tiles_total;
-  int target = 2 * g_num_sms_api;
+  int target = g_wgrad_ctas > 0 ? g_wgrad_ctas : 2 * g_num_sms_api;
   int ks = (target + base_ctas - 1) / base_ctas;
   if (ks < 1) ks = 1;
   // keep at least 8 k-steps per CTA so the pipeline fills
@@ -229,6 +230,7 @@ int clk_set_tuning(const char* key, int value) {
   if (key == nullptr) return fail(CLK_E_BADARG, "null key");
   if (strcmp(key, "fprop_bn") == 0) g_fprop_bn = value;
   else if (strcmp(key, "wgrad_ksplit") == 0) g_wgrad_ksplit = value;
+  else if (strcmp(key, "wgrad_ctas") == 0) g_wgrad_ctas = value;
   else if (strcmp(key, "wgrad_bn") == 0) g_wgrad_bn = (value == 128 ? 128 : 64);
   else if (strcmp(key, "wgrad_v2") == 0) g_wgrad_v2 = value;
   else if (strcmp(key, "conv3_v2") == 0) g_conv3_v2 = value;
