@@ -65,6 +65,7 @@ SIGNATURES = {
     "clk_ce_kd_loss": [p, p, p, ll, i, i, f, f, f, p, i, p, p, p],
     "clk_confusion_matrix": [p, p, ll, i, p, p, p],
     "clk_argmax_confusion": [p, p, ll, i, i, p, p, p, p],
+    "clk_confusion_matrix_batched": [p, p, i, ll, i, p, p, p],
     "clk_voc_prepare_batch": [p, i, i, i, p, p, p, p],
     "clk_labels_to_rgb": [p, ll, ll, p, p],
     "clk_adam_multi_tensor": [p, p, i, i, f, f, f, f, f, f, f, p, p],

@@ -556,6 +556,16 @@ int clk_head_loss_bwd(const void* z, const void* wf, const void* wd, const float
 }
 
 // ------------------------------------------------------------------ data contract around the step
+int clk_confusion_matrix_batched(const int64_t* target, const int64_t* pred, int B, long long n, int nc, int64_t* conf,
+                                 int* err_flag, clk_stream_t st) {
+  if (!target || !pred || !conf || B < 0 || n < 0 || nc < 1) return fail(CLK_E_BADARG, "confusion_matrix_batched: bad args");
+  if (nc > 38) return fail(CLK_E_UNSUPPORTED_SHAPE, "confusion_matrix_batched: nc <= 38 (nc=%d)", nc);
+  return cuda_status(confusion_matrix_batched(reinterpret_cast<const long long*>(target),
+                                              reinterpret_cast<const long long*>(pred), B, n, nc,
+                                              reinterpret_cast<long long*>(conf), err_flag, S(st)),
+                     "confusion_matrix_batched");
+}
+
 int clk_voc_prepare_batch(const void* items, int B, int H, int W, float* x, int64_t* y, int* err_flag,
                           clk_stream_t st) {
   if (!items || B < 0 || H <= 0 || W <= 0 || (!x && !y)) return fail(CLK_E_BADARG, "voc_prepare_batch: bad args");

@@ -1685,4 +1685,41 @@ cudaError_t labels_to_rgb(const long long* labels, long long n_images, long long
   return cudaGetLastError();
 }
 
+// per-image confusion matrices: conf[b][t][p] for image b, one shared-memory histogram per
+// warp; blockIdx.y = image.  Labels outside [0, nc) in EITHER map set *err_flag (the legacy metrics of
+// metrics.py:74-183 build their class lists with np.unique over both maps, so every value matters).
+__global__ void __launch_bounds__(kHistThreads)
+    confusion_batched_kernel(const long long* __restrict__ target, const long long* __restrict__ pred, long long n,
+                             int nc, unsigned long long* __restrict__ conf, int* __restrict__ err_flag) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ unsigned int sh[];  // [copies][nc*nc]
+  const int nbins = nc * nc;
+  const int copies = kHistThreads / 32;
+  for (int i = threadIdx.x; i < copies * nbins; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  unsigned int* mine = sh + (threadIdx.x >> 5) * nbins;
+  const long long* t = target + static_cast<long long>(blockIdx.y) * n;
+  const long long* q = pred + static_cast<long long>(blockIdx.y) * n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long a = t[i], b = q[i];
+    if (a >= 0 && a < nc && b >= 0 && b < nc) atomicAdd(mine + a * nc + b, 1u);
+    else if (err_flag) *err_flag = 1;
+  }
+  hist_flush(sh, nbins, copies, conf + static_cast<long long>(blockIdx.y) * nbins);
+}
+cudaError_t confusion_matrix_batched(const long long* target, const long long* pred, int B, long long n, int nc,
+                                     long long* conf, int* err_flag, cudaStream_t st) {
+  if (B <= 0 || n <= 0) return cudaSuccess;
+  const size_t smem = static_cast<size_t>(kHistThreads / 32) * nc * nc * sizeof(unsigned int);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  long long gx = (n + kHistThreads * 8 - 1) / (kHistThreads * 8);
+  if (gx > 64) gx = 64;
+  if (gx < 1) gx = 1;
+  launch_k(confusion_batched_kernel, dim3(static_cast<unsigned>(gx), B), dim3(kHistThreads), smem, st, target, pred, n, nc,
+           reinterpret_cast<unsigned long long*>(conf), err_flag);
+  return cudaGetLastError();
+}
+
 }  // namespace clk

@@ -77,4 +77,7 @@ cudaError_t voc_prepare_batch(const void* items, int B, int H, int W, float* x, 
                               cudaStream_t st);
 cudaError_t labels_to_rgb(const long long* labels, long long n_images, long long hw, double* rgb, cudaStream_t st);
 
+cudaError_t confusion_matrix_batched(const long long* target, const long long* pred, int B, long long n, int nc,
+                                     long long* conf, int* err_flag, cudaStream_t st);
+
 }  // namespace clk

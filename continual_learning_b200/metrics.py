@@ -96,3 +96,85 @@ def predict_and_count(logits_nchw_view, labels, num_classes_hist=None):
     z = z.float()
     pred, conf, correct = ops.argmax_confusion(z, labels.contiguous(), nc=num_classes_hist, want_pred=True)
     return pred, correct, (None if conf is None else conf.view(num_classes_hist, num_classes_hist))
+
+
+# ------------------------------------------------------------------------------------------------
+# Legacy per-image metrics (metrics.py:74-183; commented out at trainer.py:190).  The reference builds one boolean
+# mask per class and image in numpy; here ONE batched histogram launch counts a confusion matrix per image and the
+# four numbers follow from its row sums t_i, column sums e_i and diagonal n_ii with the reference's float64 formulas.
+class EvalSegErr(Exception):
+    def __init__(self, value):
+        self.value = value
+
+    def __str__(self):
+        return repr(self.value)
+
+
+def per_image_conf_matrices(eval_segm, gt_segm, num_classes=22):
+    """int64 [B, nc, nc] (rows = ground truth) for label maps [B, H, W] (or [H, W]); numpy or torch."""
+    e = torch.as_tensor(eval_segm)
+    g = torch.as_tensor(gt_segm)
+    if e.dim() == 2:
+        e, g = e[None], g[None]
+    if e.dim() != 3 or tuple(e.shape) != tuple(g.shape):
+        raise EvalSegErr("DiffDim: Different dimensions of matrices!")  # metrics.py:check_size
+    e = _need_cuda(e).long().contiguous()
+    g = _need_cuda(g).long().contiguous()
+    _lib.ensure_device(e.device.index)
+    b, n = e.shape[0], e.shape[1] * e.shape[2]
+    conf = torch.zeros((b, num_classes, num_classes), device=e.device, dtype=torch.int64)
+    err = torch.zeros(1, device=e.device, dtype=torch.int32)
+    _lib.call("clk_confusion_matrix_batched", g, e, b, n, num_classes, conf, err)
+    if int(err.item()):
+        raise ValueError(f"label outside [0, {num_classes}) in the evaluated or the ground-truth map")
+    return conf
+
+
+def _legacy_from_matrix(m, area):
+    """(pixel_accuracy, mean_accuracy, mean_IU, frequency_weighted_IU) of one image from its int64 matrix."""
+    t = m.sum(axis=1).astype(np.float64)   # t_i  (float64 like the reference's mask sums)
+    e = m.sum(axis=0).astype(np.float64)   # sum_j n_ji
+    d = np.diagonal(m)                     # n_ii (int64 like np.sum(logical_and))
+    gt_cl = [i for i in range(len(t)) if t[i] > 0]
+    union = [i for i in range(len(t)) if t[i] > 0 or e[i] > 0]
+    sum_n, sum_t = 0, 0
+    for i in gt_cl:
+        sum_n += d[i]
+        sum_t += t[i]
+    pa = 0 if sum_t == 0 else sum_n / sum_t
+    acc = [d[i] / t[i] for i in gt_cl]
+    ma = np.mean(acc)
+    iu = [(d[i] / (t[i] + e[i] - d[i])) if (e[i] != 0 and t[i] != 0) else 0 for i in union]
+    miu = np.sum(iu) / len(gt_cl)
+    fw = [((t[i] * d[i]) / (t[i] + e[i] - d[i])) if (e[i] != 0 and t[i] != 0) else 0 for i in union]
+    fwiu = np.sum(fw) / area
+    return pa, ma, miu, fwiu
+
+
+def legacy_metrics_batched(eval_segm, gt_segm, num_classes=22):
+    """the four legacy metrics for every image of a batch: float64 array [B, 4]
+    (pixel_accuracy, mean_accuracy, mean_IU, frequency_weighted_IU)."""
+    conf = per_image_conf_matrices(eval_segm, gt_segm, num_classes).cpu().numpy()
+    e = torch.as_tensor(eval_segm)
+    area = e.shape[-2] * e.shape[-1]
+    return np.array([_legacy_from_matrix(m, area) for m in conf], dtype=np.float64)
+
+
+def pixel_accuracy(eval_segm, gt_segm):
+    """sum_i(n_ii) / sum_i(t_i)   (metrics.py:74-98)"""
+    return legacy_metrics_batched(eval_segm, gt_segm)[0, 0]
+
+
+def mean_accuracy(eval_segm, gt_segm):
+    """(1/n_cl) sum_i(n_ii/t_i)   (metrics.py:100-124)"""
+    return legacy_metrics_batched(eval_segm, gt_segm)[0, 1]
+
+
+def mean_IU(eval_segm, gt_segm):
+    """(1/n_cl) * sum_i(n_ii / (t_i + sum_j(n_ji) - n_ii))   (metrics.py:126-153)"""
+    return legacy_metrics_batched(eval_segm, gt_segm)[0, 2]
+
+
+def frequency_weighted_IU(eval_segm, gt_segm):
+    """sum_k(t_k)^(-1) * sum_i((t_i*n_ii)/(t_i + sum_j(n_ji) - n_ii))   (metrics.py:155-183)"""
+    return legacy_metrics_batched(eval_segm, gt_segm)[0, 3]

@@ -224,6 +224,12 @@ int clk_voc_prepare_batch(const void* items, int B, int H, int W, float* x, int6
  * f64 [B][3][hw] palette colours; indices outside [0, 22) keep their value in all three channels. */
 int clk_labels_to_rgb(const int64_t* labels, long long n_images, long long hw, double* rgb, clk_stream_t st);
 
+/* One confusion matrix PER IMAGE: the counts behind the legacy per-image metrics
+ * pixel_accuracy / mean_accuracy / mean_IU / frequency_weighted_IU (metrics.py:74-183).  target, pred: int64 [B][n];
+ * conf: int64 [B][nc*nc] += (rows = target); a value outside [0, nc) in either map sets *err_flag. */
+int clk_confusion_matrix_batched(const int64_t* target, const int64_t* pred, int B, long long n, int nc, int64_t* conf,
+                                 int* err_flag, clk_stream_t st);
+
 #ifdef __cplusplus
 }
 #endif

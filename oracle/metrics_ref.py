@@ -55,3 +55,45 @@ def mean_iu_binary(target, prediction):
     t = np.asarray(target) != 0
     p = np.asarray(prediction) != 0
     return np.sum(t & p) / np.sum(t | p)
+
+
+# ---- legacy per-image metrics (metrics.py:74-183), restated with the reference's per-class boolean masks
+def _masks(segm, cl):
+    return [(segm == c) for c in cl]
+
+
+def legacy_metrics(eval_segm, gt_segm):
+    """(pixel_accuracy, mean_accuracy, mean_IU, frequency_weighted_IU) of one image pair, numpy [H, W]."""
+    eval_segm, gt_segm = np.asarray(eval_segm), np.asarray(gt_segm)
+    if eval_segm.shape != gt_segm.shape:
+        raise ValueError("DiffDim: Different dimensions of matrices!")
+    gt_cl = np.unique(gt_segm)                                   # extract_classes(gt)
+    union = np.union1d(np.unique(eval_segm), gt_cl)              # union_classes
+    # pixel_accuracy, metrics.py:74-98
+    sum_n, sum_t = 0, 0
+    for c in gt_cl:
+        em, gm = (eval_segm == c), (gt_segm == c)
+        sum_n += np.sum(np.logical_and(em, gm))
+        sum_t += np.sum(gm.astype(np.float64))
+    pa = 0 if sum_t == 0 else sum_n / sum_t
+    # mean_accuracy, metrics.py:100-124
+    acc = [0] * len(gt_cl)
+    for i, c in enumerate(gt_cl):
+        em, gm = (eval_segm == c), (gt_segm == c)
+        t_i = np.sum(gm.astype(np.float64))
+        if t_i != 0:
+            acc[i] = np.sum(np.logical_and(em, gm)) / t_i
+    ma = np.mean(acc)
+    # mean_IU / frequency_weighted_IU, metrics.py:126-183
+    iu, fw = [0] * len(union), [0] * len(union)
+    for i, c in enumerate(union):
+        em, gm = (eval_segm == c).astype(np.float64), (gt_segm == c).astype(np.float64)
+        if np.sum(em) == 0 or np.sum(gm) == 0:
+            continue
+        n_ii = np.sum(np.logical_and(em, gm))
+        t_i, n_ij = np.sum(gm), np.sum(em)
+        iu[i] = n_ii / (t_i + n_ij - n_ii)
+        fw[i] = (t_i * n_ii) / (t_i + n_ij - n_ii)
+    miu = np.sum(iu) / len(gt_cl)
+    fwiu = np.sum(fw) / (eval_segm.shape[0] * eval_segm.shape[1])
+    return pa, ma, miu, fwiu
