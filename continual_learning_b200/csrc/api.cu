@@ -320,8 +320,13 @@ static int conv3x3_fprop_impl(const void* x0, int C0, const void* x1, int C1, co
     q.bn_scale = bn_scale;
     q.bn_shift = bn_shift;
     CUtensorMap a0, a1, b;
-    const int bw = (pair && BNq == 256) ? 16 : 24;
-    if (pair && BNq != 256) {  // two sub tiles per CTA: the pair covers 16 x 32 pixels
+    int sub = BNq == 256 ? 1 : 2;
+    if (pair && BNq == 256 && 2 * q.m_tiles * q.n_tiles <= g_num_sms_api / 2) {
+      BNq = 128;  // fewer tiles than half the clusters: split N finer (one 16x16-pixel sub tile, 128 columns)
+      q.n_tiles = Cout / BNq;
+    }
+    const int bw = (pair && sub == 1) ? 16 : 24;
+    if (pair && sub == 2) {  // two sub tiles per CTA: the pair covers 16 x 32 pixels
       q.tiles_w = (W + 31) / 32;
       q.m_tiles = N * q.tiles_h * q.tiles_w;
     }
@@ -329,7 +334,7 @@ static int conv3x3_fprop_impl(const void* x0, int C0, const void* x1, int C1, co
     if (x1) CHECK_RC(map_nhwc(&a1, x1, N, H, W, C1, bw, 18, 1));
     else a1 = a0;
     CHECK_RC(map_weights(&b, w, 9, Cout, C0 + C1, pair ? BNq / 2 : BNq));
-    if (pair) return cuda_status(launch_conv3x2(BNq, a0, a1, b, q, g_num_sms_api, S(st)), "conv3x3_fprop(pair)");
+    if (pair) return cuda_status(launch_conv3x2(BNq, sub, a0, a1, b, q, g_num_sms_api, S(st)), "conv3x3_fprop(pair)");
     return cuda_status(launch_conv3(BNq, a0, a1, b, q, g_num_sms_api, S(st)), "conv3x3_fprop(halo)");
   }
   FpropParams p;
@@ -397,13 +402,18 @@ int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C
     q.dst1 = dx1;
     q.ldc1 = C1;
     CUtensorMap a0, b;
-    if (pair && BNq != 256) {
+    int sub = BNq == 256 ? 1 : 2;
+    if (pair && BNq == 256 && 2 * q.m_tiles * q.n_tiles <= g_num_sms_api / 2) {
+      BNq = 128;  // fewer tiles than half the clusters: split N finer (one 16x16-pixel sub tile, 128 columns)
+      q.n_tiles = Cin2 / BNq;
+    }
+    if (pair && sub == 2) {
       q.tiles_w = (W + 31) / 32;
       q.m_tiles = N * q.tiles_h * q.tiles_w;
     }
-    CHECK_RC(map_nhwc(&a0, dy, N, H, W, Cout, (pair && BNq == 256) ? 16 : 24, 18, 1));
+    CHECK_RC(map_nhwc(&a0, dy, N, H, W, Cout, (pair && sub == 1) ? 16 : 24, 18, 1));
     CHECK_RC(map_weights(&b, wd, 9, Cin2, Cout, pair ? BNq / 2 : BNq));
-    if (pair) return cuda_status(launch_conv3x2(BNq, a0, a0, b, q, g_num_sms_api, S(st)), "conv3x3_dgrad(pair)");
+    if (pair) return cuda_status(launch_conv3x2(BNq, sub, a0, a0, b, q, g_num_sms_api, S(st)), "conv3x3_dgrad(pair)");
     return cuda_status(launch_conv3(BNq, a0, a0, b, q, g_num_sms_api, S(st)), "conv3x3_dgrad(halo)");
   }
   FpropParams p;

@@ -1479,11 +1479,13 @@ static cudaError_t launch_conv3x2_t(const CUtensorMap& a0, const CUtensorMap& a1
 
 // BN = 256: one sub tile per CTA (a0/a1 box {64, 16, 18}, tiles of 16x16 px per pair);
 // BN = 128 / 64: two sub tiles per CTA (box {64, 24, 18}, tiles of 16x32 px per pair).  b box {64, BN/2, 1}.
-cudaError_t launch_conv3x2(int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
+// BN = 128 with one sub tile: for layers with so few 256-column tiles that half of the clusters would idle.
+cudaError_t launch_conv3x2(int BN, int SUB, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const Conv3Params& p, int num_sms, cudaStream_t st) {
-  if (BN == 256) return launch_conv3x2_t<256, 1>(a0, a1, b, p, num_sms, st);
-  if (BN == 128) return launch_conv3x2_t<128, 2>(a0, a1, b, p, num_sms, st);
-  if (BN == 64) return launch_conv3x2_t<64, 2>(a0, a1, b, p, num_sms, st);
+  if (BN == 256 && SUB == 1) return launch_conv3x2_t<256, 1>(a0, a1, b, p, num_sms, st);
+  if (BN == 128 && SUB == 2) return launch_conv3x2_t<128, 2>(a0, a1, b, p, num_sms, st);
+  if (BN == 128 && SUB == 1) return launch_conv3x2_t<128, 1>(a0, a1, b, p, num_sms, st);  // few tiles: finer N split
+  if (BN == 64 && SUB == 2) return launch_conv3x2_t<64, 2>(a0, a1, b, p, num_sms, st);
   return cudaErrorInvalidValue;
 }
 
