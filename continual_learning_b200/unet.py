@@ -109,6 +109,11 @@ class UNet(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("continual_learning_b200.UNet needs CUDA tensors (sm_100a); there is no CPU fallback")
         eng = self.engine
+        if self.conv_dim != 64:  # the one-kernel head needs the reference's 64 head input channels
+            logits = eng.forward(x, training=self.training, save_for_backward=False)
+            out = ops.argmax_confusion(logits, labels.contiguous(), nc, want_pred=want_pred, conf=conf, correct=correct)
+            eng.release()
+            return out
         z = eng.forward(x, training=self.training, save_for_backward=False, head=False)
         out = ops.head_argmax_confusion(z, eng.hwf, eng.head.bias.detach(), labels.contiguous(), self.num_classes, nc=nc,
                                         want_pred=want_pred, conf=conf, correct=correct)
