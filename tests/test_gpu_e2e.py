@@ -314,3 +314,29 @@ def test_step_host_pinned_inputs_prefetch_and_deferred_loss(clk):
     # same kernels, same order: only the fp32 atomics of the weight gradients reorder sums between runs
     np.testing.assert_allclose(runs[0], runs[1], rtol=5e-3)
     np.testing.assert_allclose(runs[0], runs[2], rtol=5e-3)
+
+
+def test_wider_model_conv_dim_128_takes_the_unfused_head_paths(clk):
+    """conv_dim = 128 (the constructor argument of models/unet.py:41): the fused head kernels need 64 head input
+    channels, so TrainStep and evaluate_batch fall back to the separate head / loss launches; numbers against the
+    fp32 oracle at a 2x64x64 batch."""
+    sd = make_state_dict(4, 21, 3, 128)
+    x, y = structured_batch(9, 2, 64, 64)
+    m = clk.UNet(21, conv_dim=128).cuda()
+    m.load_state_dict(sd)
+    m.train()
+    loss_ref, logits_ref, grads_ref, _ = step_ref.forward_backward(clone_sd(sd), x, y, conv_dim=128)
+    out = m(x.cuda())
+    assert rel(out, logits_ref) <= 5e-2
+    ts = clk.TrainStep(m, clk.FusedAdam(m.parameters(), lr=1e-4, betas=(0.5, 0.99)), use_graph=False)
+    assert not ts.fused_head
+    m2 = clk.UNet(21, conv_dim=128).cuda()
+    m2.load_state_dict(sd)
+    m2.train()
+    ts2 = clk.TrainStep(m2, clk.FusedAdam(m2.parameters(), lr=1e-4, betas=(0.5, 0.99)), use_graph=False)
+    loss = float(ts2.step(x.cuda(), y.cuda()))
+    assert abs(loss - loss_ref) <= 3e-3 * loss_ref
+    m2.eval()
+    pred, conf, ok = m2.evaluate_batch(x.cuda(), y.cuda(), nc=21, want_pred=True)
+    with torch.no_grad():
+        assert torch.equal(pred, m2(x.cuda()).argmax(1)) and int(conf.sum()) == y.numel()
