@@ -98,3 +98,55 @@ def to_rgb(xs):
     out = torch.empty((b, 3, h, w), device=xs.device, dtype=torch.float64)
     _lib.call("clk_labels_to_rgb", xs, b, h * w, out)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Dataset side: the reference's file handling (datasets/voc.py:91-148) with the per-pixel work moved to the device.
+class VOCDecoded(torch.utils.data.Dataset):
+    """`datasets.voc.VOC` up to and including the PIL decode: same directory layout and file lists
+    (`make_path`, datasets/voc.py:91-113 — like the reference, 'val' also reads train.txt), same
+    `Image.open(...).convert('RGB')` (datasets/voc.py:129-130); returns the two decoded uint8 [H, W, 3] arrays.
+    Pad / CenterCrop / ToTensor / Normalize / to_mask happen per batch in `prepare_batch`."""
+
+    def __init__(self, root, dataset_type="train"):
+        import os
+        assert dataset_type in ["train", "val"], "dataset_type should be in train/val"
+        img_path = os.path.join(root, "VOC2012", "JPEGImages")
+        mask_path = os.path.join(root, "VOC2012", "SegmentationClass")
+        with open(os.path.join(root, "VOC2012", "ImageSets", "Segmentation", "train.txt")) as f:
+            names = [line.strip("\n") for line in f.readlines()]
+        self.items = [(os.path.join(img_path, n + ".jpg"), os.path.join(mask_path, n + ".png")) for n in names]
+        self.dataset_type = dataset_type
+
+    def __len__(self):
+        return len(self.items)
+
+    def __getitem__(self, i):
+        import numpy as np
+        from PIL import Image
+        name = self.items[i]
+        image = np.asarray(Image.open(name[0]).convert("RGB"))
+        mask = np.asarray(Image.open(name[1]).convert("RGB"))
+        return torch.from_numpy(np.ascontiguousarray(image)), torch.from_numpy(np.ascontiguousarray(mask))
+
+
+class DeviceBatches:
+    """DataLoader-like iterable over a dataset of decoded (image, mask) uint8 pairs that yields the batches the
+    reference's DataLoader would have produced, built on the device by `prepare_batch`:
+    (x fp32 [B, 3, h, w] in [-1, 1], y int64 [B, h, w]), both CUDA tensors."""
+
+    def __init__(self, dataset, batch_size, image_size, shuffle=False, drop_last=False, num_workers=0, device=None):
+        self.dataset = dataset
+        self.h, self.w = int(image_size[0]), int(image_size[1])
+        self.device = device
+        self.loader = torch.utils.data.DataLoader(dataset, batch_size=batch_size, shuffle=shuffle, drop_last=drop_last,
+                                                  num_workers=num_workers, collate_fn=list, pin_memory=False)
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        for batch in self.loader:
+            images = [b[0] for b in batch]
+            masks = [b[1] for b in batch]
+            yield prepare_batch(images, masks, self.h, self.w, device=self.device)

@@ -4,7 +4,8 @@
     python main.py --mode train --train_batch_size 16 --h_image_size 256 --w_image_size 256 --synthetic
     python -m torch.distributed.run --nproc-per-node 8 main.py ... --train_batch_size 128   # batch sharded by rank
 
-Additive flags: --synthetic/--synthetic_size (seeded VOC-shaped data, no dataset on disk), the continual-learning
+Additive flags: --synthetic/--synthetic_size (seeded VOC-shaped data, no dataset on disk), --device_preprocess
+(VOC files decoded on the host, everything per-pixel on the GPU), the continual-learning
 options (--old_model_path, --num_old_classes, --distill_T, --distill_lambda) and --seed.
 """
 import argparse
@@ -33,6 +34,15 @@ def get_loader(config):
     """train / "val" loaders (main.py:17-43; like the reference the val loader iterates the training set)."""
     if config.synthetic:
         ds = SyntheticVOC(config.synthetic_size, config.h_image_size, config.w_image_size)
+    elif config.device_preprocess:
+        # same files, same PIL decode; Pad / CenterCrop / ToTensor / Normalize / to_mask run on the GPU per batch
+        from continual_learning_b200 import voc
+        ds = voc.VOCDecoded(config.path, "train")
+        size = (config.h_image_size, config.w_image_size)
+        train = voc.DeviceBatches(ds, config.train_batch_size, size, shuffle=True, drop_last=True,
+                                  num_workers=config.num_workers)
+        val = voc.DeviceBatches(ds, config.val_batch_size, size, shuffle=False, num_workers=config.num_workers)
+        return train, val
     else:
         from torchvision import transforms
         from datasets.voc import VOC  # the reference's dataset module (not part of this package)
@@ -81,6 +91,9 @@ def build_parser():
     # additive
     p.add_argument("--synthetic", action="store_true", help="seeded synthetic VOC-shaped data instead of --path")
     p.add_argument("--synthetic_size", type=int, default=64)
+    p.add_argument("--device_preprocess", action="store_true",
+                   help="decode VOC files with PIL like datasets/voc.py, do the per-pixel work (crop, normalise, "
+                        "palette -> label) on the GPU")
     p.add_argument("--old_model_path", type=str, default=None, help="checkpoint of the frozen previous-task network")
     p.add_argument("--num_old_classes", type=int, default=16)
     p.add_argument("--distill_T", type=float, default=2.0)

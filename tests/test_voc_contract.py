@@ -97,3 +97,70 @@ def test_to_rgb_matches_reference_golden_and_oracle(gold, lib_built):
     rng = np.random.Generator(np.random.PCG64(6))
     labels = rng.integers(-2, 30, size=(4, 64, 48))
     assert np.array_equal(voc.to_rgb(torch.from_numpy(labels).cuda()).cpu().numpy(), voc_ref.to_rgb(labels))
+
+
+def _fake_voc_tree(root, sizes, seed=17):
+    """a miniature VOC2012 directory (datasets/voc.py:91-113 layout) with random JPEG images and palette PNG masks"""
+    from PIL import Image
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base = os.path.join(root, "VOC2012")
+    for sub in ("JPEGImages", "SegmentationClass", os.path.join("ImageSets", "Segmentation")):
+        os.makedirs(os.path.join(base, sub), exist_ok=True)
+    pal = np.asarray(voc_ref.PALETTE, dtype=np.uint8)
+    names = []
+    for k, (hs, ws) in enumerate(sizes):
+        name = f"2007_{k:06d}"
+        names.append(name)
+        Image.fromarray(rng.integers(0, 256, size=(hs, ws, 3), dtype=np.uint8)).save(
+            os.path.join(base, "JPEGImages", name + ".jpg"), quality=90)
+        cls = np.kron(rng.integers(0, 22, size=(hs // 8 + 1, ws // 8 + 1)), np.ones((8, 8), dtype=np.int64))[:hs, :ws]
+        Image.fromarray(pal[cls]).save(os.path.join(base, "SegmentationClass", name + ".png"))
+    with open(os.path.join(base, "ImageSets", "Segmentation", "train.txt"), "w") as f:
+        f.write("\n".join(names) + "\n")
+    return names
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference checkout is only in the build container")
+def test_decoded_dataset_plus_oracle_equals_the_reference_dataset_class(tmp_path):
+    """live pin of the whole `VOC.__getitem__` (file lists, PIL decode, transforms, to_mask) where the reference exists:
+    reference dataset == VOCDecoded (same files, same decode) + oracle.prepare_sample, bit for bit"""
+    import sys
+    sys.path.insert(0, "/root/reference")
+    try:
+        from torchvision import transforms
+        from datasets.voc import VOC
+    finally:
+        sys.path.remove("/root/reference")
+    from continual_learning_b200 import voc
+    sizes = [(60, 80), (33, 47), (90, 50), (20, 30)]
+    _fake_voc_tree(str(tmp_path), sizes)
+    h, w = 48, 40
+    tf = transforms.Compose([transforms.Pad(10), transforms.CenterCrop((h, w)), transforms.ToTensor(),
+                             transforms.Normalize(mean=(0.5, 0.5, 0.5), std=(0.5, 0.5, 0.5))])  # main.py:17-22
+    ref_ds = VOC(root=str(tmp_path), image_size=(h, w), dataset_type="train", transform=tf)
+    ds = voc.VOCDecoded(str(tmp_path), "train")
+    assert len(ds) == len(ref_ds) == len(sizes)
+    for i in range(len(ds)):
+        xr, yr = ref_ds[i]
+        img, mask = ds[i]
+        x, y = voc_ref.prepare_sample(img.numpy(), mask.numpy(), h, w)
+        assert np.array_equal(x, xr.numpy()) and np.array_equal(y, yr.numpy()), i
+
+
+@pytest.mark.gpu
+def test_device_batches_from_files_match_the_oracle(tmp_path, lib_built):
+    from continual_learning_b200 import voc
+    sizes = [(375, 500), (500, 375), (300, 300), (120, 200), (281, 500), (256, 256)]
+    _fake_voc_tree(str(tmp_path), sizes)
+    ds = voc.VOCDecoded(str(tmp_path), "val")
+    loader = voc.DeviceBatches(ds, batch_size=4, image_size=(256, 256), shuffle=False, drop_last=False)
+    assert len(loader) == 2 and len(loader.dataset) == 6
+    k = 0
+    for x, y in loader:
+        assert x.is_cuda and x.dtype == torch.float32 and y.dtype == torch.int64
+        for b in range(x.shape[0]):
+            img, mask = ds[k]
+            xr, yr = voc_ref.prepare_sample(img.numpy(), mask.numpy(), 256, 256)
+            assert np.array_equal(x[b].cpu().numpy(), xr) and np.array_equal(y[b].cpu().numpy(), yr), k
+            k += 1
+    assert k == 6
