@@ -47,16 +47,20 @@ __device__ __forceinline__ void tile_base(const TileGeom& g, int tile, int& b1, 
 }
 
 // row m of the tile -> linear pixel index of the tiled tensor (or -1 when outside)
+// n, h, w are only produced when need_nhw (the ConvTranspose2d pixel-shuffle epilogue): the linear case would
+// otherwise pay four integer divisions per thread and tile for nothing (P < 2^31 is checked by the callers)
 __device__ __forceinline__ long long tile_row_pixel(const TileGeom& g, int b1, int b2, int b3,
-                                                    int b4, int m, int& n, int& h, int& w) {
+                                                    int b4, int m, int& n, int& h, int& w, bool need_nhw = true) {
   if (g.mode == ADDR_LINEAR) {
-    const long long pix = static_cast<long long>(b1) + m;
-    const long long P = static_cast<long long>(g.N) * g.H * g.W;
-    if (pix >= P) return -1;
-    w = static_cast<int>(pix % g.W);
-    const long long r = pix / g.W;
-    h = static_cast<int>(r % g.H);
-    n = static_cast<int>(r / g.H);
+    const unsigned int pix = static_cast<unsigned int>(b1) + static_cast<unsigned int>(m);
+    if (static_cast<long long>(pix) >= static_cast<long long>(g.N) * g.H * g.W) return -1;
+    if (need_nhw) {
+      const unsigned int W = static_cast<unsigned int>(g.W), H = static_cast<unsigned int>(g.H);
+      const unsigned int r = pix / W;
+      w = static_cast<int>(pix - r * W);
+      n = static_cast<int>(r / H);
+      h = static_cast<int>(r - static_cast<unsigned int>(n) * H);
+    }
     return pix;
   } else if (g.mode == ADDR_NHWC) {
     w = b1 + m % g.tw;
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
       int b1, b2, b3, b4;
       tile_base(p.g, t % m_tiles, b1, b2, b3, b4);
       int pn = 0, ph_ = 0, pw = 0;
-      long long pix = tile_row_pixel(p.g, b1, b2, b3, b4, m, pn, ph_, pw);
+      long long pix = tile_row_pixel(p.g, b1, b2, b3, b4, m, pn, ph_, pw, p.shuffle != 0);
       const bool valid = pix >= 0;
       OutT* dst = reinterpret_cast<OutT*>(p.dst0);
       int ld = p.ldc0;
