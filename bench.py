@@ -115,12 +115,13 @@ def measured_peaks():
 
 # ---------------------------------------------------------------------------------------------
 def cpu_step_throughput(steps, warmup, batch, threads=None, budget_s=150.0):
-    """the reference training step (trainer.py:172-176) through the CPU oracle port, fp32, all host threads
-    (torchrun exports OMP_NUM_THREADS=1: overridden here, rank 0 is the only rank doing CPU work).  Stops early when
-    the time budget is used up, so `--steps 100` still ends within a few minutes on a slow host."""
-    from oracle import step_ref
-    from oracle.data import uniform_batch
-    from oracle.unet_ref import make_state_dict, param_names
+    """the reference training step (trainer.py:172-176) on the host cores, fp32, all host threads (torchrun exports
+    OMP_NUM_THREADS=1: overridden here, rank 0 is the only rank doing CPU work).  Runs the REFERENCE'S OWN U-Net
+    module when `oracle/_ref` was staged (byte-compiled from /root/reference by `oracle/build_ref.py`; kind
+    "reference"), else the oracle port (kind "port").  Stops early when the time budget is used up, so `--steps 100`
+    still ends within a few minutes on a slow host.  Returns (img/s, s/step, threads, steps timed, kind)."""
+    from continual_learning_b200.synthetic import uniform_batch
+    from oracle import build_ref
     if threads is None:
         try:
             threads = len(os.sched_getaffinity(0))
@@ -128,20 +129,41 @@ def cpu_step_throughput(steps, warmup, batch, threads=None, budget_s=150.0):
             threads = os.cpu_count() or 1
     torch.set_num_threads(max(1, threads))
     t_begin = time.perf_counter()
-    sd = make_state_dict(0, NUM_CLASSES)
-    opt = step_ref.AdamRef(param_names(sd), lr=1e-4, betas=(0.5, 0.99))
     x, y = uniform_batch(1, batch, H, W, NUM_CLASSES)
+    if build_ref.available():
+        kind = "reference"
+        UNet, _ = build_ref.load()
+        torch.manual_seed(0)
+        model = UNet(num_classes=NUM_CLASSES, in_dim=3, conv_dim=64)                 # trainer.py:107
+        optim = torch.optim.Adam(model.parameters(), lr=1e-4, betas=[0.5, 0.99])     # trainer.py:108-110
+        c_loss = torch.nn.CrossEntropyLoss()                                         # trainer.py:113
+
+        def one_step():                                                              # trainer.py:172-176
+            outputs = model(x)
+            optim.zero_grad()
+            loss = c_loss(outputs, y)
+            loss.backward()
+            optim.step()
+    else:
+        kind = "port"
+        from oracle import step_ref
+        from oracle.unet_ref import make_state_dict, param_names
+        sd = make_state_dict(0, NUM_CLASSES)
+        opt = step_ref.AdamRef(param_names(sd), lr=1e-4, betas=(0.5, 0.99))
+
+        def one_step():
+            _, _, grads, _ = step_ref.forward_backward(sd, x, y)
+            opt.step(sd, grads)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        _, _, grads, _ = step_ref.forward_backward(sd, x, y)
-        opt.step(sd, grads)
+        one_step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
             if time.perf_counter() - t_begin > budget_s:
                 break
-    return batch / statistics.median(times), statistics.median(times), torch.get_num_threads(), len(times)
+    return batch / statistics.median(times), statistics.median(times), torch.get_num_threads(), len(times), kind
 
 
 def run_reference(args):
@@ -149,14 +171,16 @@ def run_reference(args):
     if rank != 0:
         return
     sample_batch = 2
-    val, sec, cores, ran = cpu_step_throughput(max(1, args.steps), args.warmup, sample_batch)
-    sample = (f"oracle port of trainer.py:172-176 (fp32 CPU), batch {sample_batch} of the {BATCH}-image 256x256 step, "
+    val, sec, cores, ran, kind = cpu_step_throughput(max(1, args.steps), args.warmup, sample_batch)
+    what = ("the reference's own models/unet.py UNet (oracle/_ref) + nn.CrossEntropyLoss + optim.Adam, loop of" if kind == "reference"
+            else "oracle port of")
+    sample = (f"{what} trainer.py:172-176 (fp32 CPU), batch {sample_batch} of the {BATCH}-image 256x256 step, "
               f"{ran} of {args.steps} steps timed after {args.warmup} warm-up (150 s budget), median {sec:.3f} s/step")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "note": "CPU reference arm: bounded sample (batch 2) per step"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -168,7 +192,7 @@ def run_b200(args):
 
     import continual_learning_b200 as clk
     from continual_learning_b200 import _lib, parallel
-    from oracle.data import uniform_batch
+    from continual_learning_b200.synthetic import uniform_batch
 
     rank, local, world = parallel.init_from_env()
     if world != args.gpus:
@@ -262,7 +286,7 @@ def run_b200(args):
     ms_e2e = float(t.item())
     e2e_value = world * BATCH * args.steps / (ms_e2e / 1e3)
     h2d = host[0][0].numel() * 4 + host[0][1].numel() * 8
-    d2h = 8
+    d2h = 16  # {loss, out-of-range-label flag} as two float64, one read per step
 
     # ---- per-kernel timing of one eager step (CUDA events around every clk_* launch) -> roofline
     ts_prof = clk.TrainStep(model, opt, old_model=old_model, T=2.0, lam=1.0, use_graph=False, comm=comm)
@@ -301,9 +325,10 @@ def run_b200(args):
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only): bounded sample
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, sec, cores, _ = cpu_step_throughput(steps=4, warmup=1, batch=2)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"oracle port of trainer.py:172-176, fp32, batch 2 x 256x256 (BASELINE config 1 shape), 4 steps after 1 warm-up, median {sec:.3f} s/step"}
+        v, sec, cores, _, kind = cpu_step_throughput(steps=6, warmup=2, batch=2)
+        what = "the reference's own U-Net module (oracle/_ref)" if kind == "reference" else "oracle port"
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": f"{what}, loop of trainer.py:172-176, fp32, batch 2 x 256x256 (BASELINE config 1 shape), 6 steps after 2 warm-up, median {sec:.3f} s/step"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -66,6 +66,7 @@ class UNetEngine:
         self.training_fwd = True
         self.save_for_backward = True
         self.logits = None
+        self.generation = 0  # bumped by every forward (stale-backward detection in unet._UNetFn)
 
     # ------------------------------------------------------------------ persistent buffers
     def _setup(self, dev):
@@ -296,6 +297,7 @@ class UNetEngine:
         head=False stops before the 1x1 head and returns its bf16 input [N, H, W, 64] (TrainStep fuses the head with
         the loss and the head's backward, see `head_loss_backward`)."""
         self.save_for_backward = save_for_backward
+        self.generation += 1
         if not x.is_cuda:
             raise RuntimeError("continual_learning_b200.UNet runs on CUDA (sm_100a) only: there is no CPU fallback")
         _lib.ensure_device(x.device.index)

@@ -37,10 +37,13 @@ class _LossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         dl = ctx.dl
-        dl = dl * g.to(dl.dtype) if g.numel() == 1 else dl
+        if g.numel() == 1:
+            dl.mul_(g.to(dl.dtype))  # in place: the loss owns this buffer
         eng = ctx.engine
         if eng is not None:
-            token = torch.full((1,), float('nan'), device=dl.device, dtype=torch.float32).expand(ctx.shape)
+            # the real gradient travels next to autograd as bf16 [B,H,W,64]; the returned token is all zeros so that
+            # a second consumer of `outputs` (auxiliary loss, regulariser) still sums to the right thing
+            token = torch.zeros((1,), device=dl.device, dtype=torch.float32).expand(ctx.shape)
             eng._pending_dlogits = (token, dl)
             return token, None, None, None, None, None
         c = ctx.shape[1]
@@ -55,6 +58,15 @@ class CrossEntropyDistillLoss(nn.Module):
         self.last_error_flag = None
         self._engine_hint = None
         self._old_logits = None
+
+    def check_labels(self):
+        """nn.CrossEntropyLoss raises on a label outside [0, C) (trainer.py:174); the fused kernel records it in a
+        device flag instead of stalling the stream.  Call where a host sync happens anyway (Trainer does, in its
+        every-10th-iteration statistics block): raises IndexError like the reference's CPU loss."""
+        flag = self.last_error_flag
+        if flag is not None and int(flag.item()) != 0:
+            self.last_error_flag = None
+            raise IndexError("Target out of bounds: a label outside [0, num_classes) reached the loss")
 
     def observe(self, inputs):
         """run the frozen previous-task network (eval mode, no grad) on this batch's inputs."""

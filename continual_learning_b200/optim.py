@@ -19,6 +19,33 @@ class FusedAdam(torch.optim.Optimizer):
         betas = (float(betas[0]), float(betas[1]))
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0.0))
         self._tables = {}
+        self.state_epoch = 0  # bumped whenever the state is replaced from outside (load_state_dict)
+
+    def load_state_dict(self, state_dict):
+        """torch.optim.Adam-compatible (trainer.py:98): `TrainStep` re-reads the step count afterwards so that a
+        resumed run continues the bias correction where the checkpoint stopped."""
+        super().load_state_dict(state_dict)
+        self.state_epoch += 1
+        self._tables = {}
+
+    def group_step(self, plist):
+        """the common optimiser step count of `plist` (0 before the first step); raises if they disagree."""
+        seen, steps = set(), set()
+        for p in plist:
+            t = self.state.get(p, {}).get("step")
+            if t is None:
+                steps.add(0.0)
+            elif id(t) not in seen:  # the step tensor is shared between the parameters: one read in the common case
+                seen.add(id(t))
+                steps.add(float(t))
+        if len(steps) > 1:
+            raise RuntimeError("FusedAdam expects all parameters of a group to share the step count")
+        return steps.pop() if steps else 0.0
+
+    def set_group_step(self, plist, step):
+        t = torch.tensor(float(step))
+        for p in plist:
+            self.state[p]["step"] = t
 
     def _table(self, gi, plist):
         key = (gi, tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr(),
@@ -64,12 +91,8 @@ class FusedAdam(torch.optim.Optimizer):
                     st["step"] = torch.tensor(0.0)
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-            steps = {float(self.state[p]["step"]) for p in plist}
-            if len(steps) != 1:
-                raise RuntimeError("FusedAdam expects all parameters of a group to share the step count")
-            step = steps.pop() + 1.0
-            for p in plist:
-                self.state[p]["step"] = torch.tensor(step)
+            step = self.group_step(plist) + 1.0
+            self.set_group_step(plist, step)
             b1, b2 = group["betas"]
             bc1 = 1.0 - b1 ** step
             bc2_sqrt = math.sqrt(1.0 - b2 ** step)

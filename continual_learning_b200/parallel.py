@@ -16,10 +16,12 @@ def init_from_env(backend=None):
     """torchrun-style rendezvous (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    local = int(os.environ.get("CLK_FORCE_LOCAL_RANK") or os.environ.get("LOCAL_RANK", "0"))
     if world > 1 and not dist.is_initialized():
         if backend is None:
-            backend = "nccl" if torch.cuda.is_available() else "gloo"
+            # CLK_DIST_BACKEND=gloo: several ranks sharing ONE GPU (NCCL refuses duplicate devices) — the test suite
+            # uses it to run the real N-rank code path, kernels included, on a single-GPU box
+            backend = os.environ.get("CLK_DIST_BACKEND") or ("nccl" if torch.cuda.is_available() else "gloo")
         if backend == "nccl":
             torch.cuda.set_device(local)
             dist.init_process_group(backend, device_id=torch.device("cuda", local))
@@ -28,11 +30,18 @@ def init_from_env(backend=None):
     return rank, local, world
 
 
-def shard_batch(x, rank, world):
-    """rank r takes images [r*B/n, (r+1)*B/n) of the global batch."""
+def shard_batch(x, rank, world, ragged=False):
+    """rank r takes images [r*B/n, (r+1)*B/n) of the global batch.
+
+    ragged=True (validation: the reference's val loader has no drop_last, main.py:39-41) tolerates a batch that is
+    not a multiple of the world size: the first B % n ranks take one image more, a rank may get an empty shard."""
     b = x.shape[0]
     if b % world:
-        raise ValueError(f"global batch {b} is not divisible by world size {world}")
+        if not ragged:
+            raise ValueError(f"global batch {b} is not divisible by world size {world}")
+        per, rem = divmod(b, world)
+        start = rank * per + min(rank, rem)
+        return x[start:start + per + (1 if rank < rem else 0)]
     per = b // world
     return x[rank * per:(rank + 1) * per]
 
@@ -101,12 +110,14 @@ class GradAllReduce:
 
 
 def all_reduce_confusion(conf, correct, group=None):
-    """validation sweep: one small int64 all-reduce of the confusion matrix + correct count."""
+    """validation sweep: ONE small int64 all-reduce of the confusion matrix + the counters.
+    `conf` may be empty and `correct` may hold any number of counters (correct pixels, total pixels, ...)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return conf, correct
+    n = conf.numel()
     buf = torch.cat([conf.reshape(-1), correct.reshape(-1)])
     dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    return buf[:-1].view_as(conf), buf[-1:]
+    return buf[:n].view_as(conf), buf[n:].view_as(correct)
 
 
 def attach(model, optimizer, n_buckets=4):

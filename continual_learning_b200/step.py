@@ -30,7 +30,8 @@ class TrainStep:
         self.comm = comm  # parallel.GradAllReduce or None
         self.graph = None
         self.shape = None
-        self.step_count = 0
+        self.step_count = 0       # optimiser steps taken so far; re-read from the optimiser state when it changes
+        self._opt_epoch = None    # FusedAdam.state_epoch seen at the last sync
         self.launches_per_step = 0
         self._graph_ptr = None
         self._opt_ready = False
@@ -85,6 +86,15 @@ class TrainStep:
         self.graph = None
         self._opt_ready = False
 
+    def _sync_step_count(self):
+        """Adam's bias correction uses the optimiser's own step count: pick it up from the state on first use and
+        after `load_state_dict` (resume, trainer.py:98), so that a warm exp_avg / exp_avg_sq is not corrected as t=1."""
+        if self._opt_epoch == self.opt.state_epoch:
+            return
+        self._opt_epoch = self.opt.state_epoch
+        plist = [p for g in self.opt.param_groups for p in g["params"]]
+        self.step_count = int(self.opt.group_step(plist))
+
     def _set_hyper(self):
         gs = 1.0 if self.comm is None else 1.0 / self.comm.world_size
         vals = self.opt.hyper_values(self.step_count + 1, grad_scale=gs)
@@ -95,6 +105,7 @@ class TrainStep:
         """x fp32 [B,3,H,W], y int64 [B,H,W], both on the device. Returns the loss as a 0-dim fp64 device tensor."""
         if self.shape != (tuple(x.shape), tuple(y.shape)):
             self._alloc(x, y)
+        self._sync_step_count()
         self._set_hyper()
         if not self.use_graph:
             self._body(x, y)
@@ -128,9 +139,7 @@ class TrainStep:
                 self._restore(state)
             self.graph.replay()
         self.step_count += 1
-        for p in self.model.engine.params:
-            st = self.opt.state[p]
-            st["step"] = torch.tensor(float(self.step_count))
+        self.opt.set_group_step(self.model.engine.params, self.step_count)
         loss = self.loss_acc[0] / self.npix
         if self.old is not None:
             loss = loss + (self.lam * self.T * self.T / self.npix) * self.loss_acc[1]
@@ -168,15 +177,17 @@ class TrainStep:
         loss = self.step(x, y)
         x.record_stream(torch.cuda.current_stream())
         y.record_stream(torch.cuda.current_stream())
+        # {loss, out-of-range-label flag}: ONE device->host read per step
+        res = torch.stack((loss, self.err_flag[0].double()))
         if not defer_loss:
-            return float(loss.item())
+            return self._checked(res.cpu())
         if getattr(self, "_loss_host", None) is None:
-            self._loss_host = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in range(2)]
+            self._loss_host = [torch.zeros(2, dtype=torch.float64).pin_memory() for _ in range(2)]
             self._loss_ev = [None, None]
             self._loss_k = 0
         prev = self.flush_loss()
         k = self._loss_k & 1
-        self._loss_host[k].copy_(loss.reshape(1), non_blocking=True)
+        self._loss_host[k].copy_(res, non_blocking=True)
         self._loss_ev[k] = torch.cuda.Event()
         self._loss_ev[k].record()
         self._loss_pending = k
@@ -190,7 +201,15 @@ class TrainStep:
             return None
         self._loss_ev[k].synchronize()
         self._loss_pending = None
-        return float(self._loss_host[k][0])
+        return self._checked(self._loss_host[k])
+
+    def _checked(self, res):
+        """res = host {loss, label-error flag}: raise like nn.CrossEntropyLoss (trainer.py:174) on a label outside
+        [0, num_classes) — such pixels contribute nothing to the loss or the gradient of that step."""
+        if float(res[1]) != 0.0:
+            self.err_flag.zero_()
+            raise IndexError("Target out of bounds: a label outside [0, num_classes) reached the loss")
+        return float(res[0])
 
     # the capture warm-up and the capture itself run the step body for real: undo their effect on the
     # parameters, optimiser state and BatchNorm buffers so that step k of a graph run equals step k eagerly
@@ -214,4 +233,4 @@ class TrainStep:
                     # state was created during the warm-up: reset it to Adam's initial state
                     st["exp_avg"].zero_()
                     st["exp_avg_sq"].zero_()
-                st["step"] = torch.tensor(float(self.step_count))
+        self.opt.set_group_step([p for p in self.model.parameters() if p in self.opt.state], self.step_count)

@@ -139,6 +139,7 @@ class Trainer:
                 if I % 10 == 0:
                     print_number += 1
                     curr_loss = loss.item()
+                    self.c_loss.check_labels()  # a label outside [0, 21) raises like nn.CrossEntropyLoss
                     running_loss += curr_loss
                     # argmax(softmax(x)) == argmax(x): one fused pass gives predictions, correct count and the
                     # 22x22 confusion matrix of trainer.py:183-188
@@ -198,9 +199,11 @@ class Trainer:
         with torch.no_grad():
             for images, labels in self.val_data_loader:
                 images, labels = images.to(self.device), labels.to(self.device)
-                if self.world > 1:
-                    images = parallel.shard_batch(images, self.rank, self.world)
-                    labels = parallel.shard_batch(labels, self.rank, self.world)
+                if self.world > 1:  # no drop_last on the val loader (main.py:39-41): the last batch may be ragged
+                    images = parallel.shard_batch(images, self.rank, self.world, ragged=True)
+                    labels = parallel.shard_batch(labels, self.rank, self.world, ragged=True)
+                if images.shape[0] == 0:
+                    continue
                 # forward + head + argmax + correct count in inference mode, logits never materialised
                 self.model.evaluate_batch(images, labels, correct=correct)
                 total += labels.nelement()

@@ -38,16 +38,27 @@ class _UNetFn(torch.autograd.Function):
     def forward(ctx, x, engine, training, *params):
         logits = engine.forward(x, training=training)
         ctx.engine = engine
+        ctx.generation = engine.generation  # the engine keeps the activations of its LATEST forward only
         out = logits.permute(0, 3, 1, 2)  # [B, C, H, W] view over NHWC memory
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         eng = ctx.engine
+        if ctx.generation != eng.generation:
+            raise RuntimeError("UNet.backward: another forward ran on this module since the one being differentiated; "
+                               "the engine keeps the activations of the latest forward only (forward -> backward, as "
+                               "in trainer.py:172-175)")
         pending = getattr(eng, "_pending_dlogits", None)
+        eng._pending_dlogits = None
         if pending is not None and grad_out.data_ptr() == pending[0].data_ptr():
             dl = pending[1]  # fused loss already produced bf16 [B,H,W,64] dlogits
-            eng._pending_dlogits = None
+        elif pending is not None:
+            # `outputs` had a second differentiable consumer: autograd summed its gradient with the (all-zero) token
+            # of the fused loss, so grad_out holds only the OTHER consumers' part -> add the fused loss's dlogits
+            g = grad_out.permute(0, 2, 3, 1)
+            dl = pending[1].clone()
+            dl[..., :g.shape[3]] += g.to(dl.dtype)
         else:
             g = grad_out.permute(0, 2, 3, 1)
             dl = torch.zeros((*g.shape[:3], 64), device=g.device, dtype=torch.bfloat16)

@@ -25,7 +25,7 @@ class SyntheticVOC(Dataset):
         return self.n
 
     def __getitem__(self, i):
-        from oracle.data import structured_batch
+        from continual_learning_b200.synthetic import structured_batch
         x, y = structured_batch(i, 1, self.h, self.w)
         return x[0], y[0]
 
@@ -49,8 +49,10 @@ def get_loader(config):
         tf = transforms.Compose([transforms.Pad(10), transforms.CenterCrop((config.h_image_size, config.w_image_size)),
                                  transforms.ToTensor(), transforms.Normalize(mean=(0.5,) * 3, std=(0.5,) * 3)])
         ds = VOC(root=config.path, image_size=(config.h_image_size, config.w_image_size), dataset_type="train", transform=tf)
+    # seeded shuffle: under torchrun every rank must draw the SAME global batch before taking its shard
     train = DataLoader(ds, batch_size=config.train_batch_size, shuffle=True, drop_last=True,
-                       num_workers=config.num_workers, pin_memory=True)
+                       num_workers=config.num_workers, pin_memory=True,
+                       generator=torch.Generator().manual_seed(config.seed))
     val = DataLoader(ds, batch_size=config.val_batch_size, shuffle=False, num_workers=config.num_workers, pin_memory=True)
     return train, val
 

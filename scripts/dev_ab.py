@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import continual_learning_b200 as clk
-from oracle.data import uniform_batch
+from continual_learning_b200.synthetic import uniform_batch
 
 
 def time_cfg(flags, tune, steps=40):

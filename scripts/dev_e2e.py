@@ -9,7 +9,7 @@ import torch
 
 import continual_learning_b200 as clk
 from oracle import step_ref
-from oracle.data import structured_batch
+from continual_learning_b200.synthetic import structured_batch
 from oracle.unet_ref import UNetRef, clone_sd, make_state_dict, param_names
 
 

@@ -7,7 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import continual_learning_b200 as clk
-from oracle.data import structured_batch
+from continual_learning_b200.synthetic import structured_batch
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 torch.manual_seed(0)

@@ -1,0 +1,198 @@
+"""GPU (-m gpu): ELEMENT-WISE parity at BASELINE.json's full sizes (batch 16, 256x256).
+
+The CPU oracle would take minutes at these sizes, so the checker here is the same arithmetic run in fp32 ON THE
+GPU with TF32 disabled (stock `F.conv2d` + autograd for the layers; `oracle.unet_ref.UNetRef` — the functional
+restatement of models/unet.py:74-92 pinned against the reference modules in tests/test_oracle_pinned.py — moved to
+the device for the whole step).  cuDNN/ATen are used as CHECKERS only; nothing of this is on the product path.
+
+  * every distinct conv3x3 layer shape of the training step (Appendix A of SURVEY.md): forward (+bias, ReLU and the
+    BatchNorm statistics of the epilogue), data gradient (both destinations of a folded concat) and weight gradient,
+    rel-L2 AND a per-element bound (a wrong tile, row or halo column cannot hide in a norm);
+  * the whole step at 16x256x256 on structured data: loss, logits, every parameter's gradient against the fp32 run
+    with SURVEY.md §8(c)'s tolerances (loss 1e-3, logits rel-L2 3e-2, global gradient rel-L2 3e-2 / cosine 0.999).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+bf16 = torch.bfloat16
+BF16_TOL = 3e-3   # one bf16 output rounding (2^-9 rms) on top of fp32 accumulation
+
+LAYERS = [  # (H=W, c0, c1, cout) at batch 16: all 3x3 layers of models/unet.py:50-71 except the 3-channel stem
+    (256, 64, 0, 64), (256, 64, 64, 64),
+    (128, 64, 0, 128), (128, 128, 0, 128), (128, 128, 128, 128),
+    (64, 128, 0, 256), (64, 256, 0, 256), (64, 256, 256, 256),
+    (32, 256, 0, 512), (32, 512, 0, 512), (32, 512, 512, 512),
+    (16, 512, 0, 1024), (16, 1024, 0, 1024),
+]
+
+
+@pytest.fixture(scope="module")
+def ops(lib_built):
+    from continual_learning_b200 import _lib, ops as _ops
+    _lib.ensure_device(0)
+    return _ops
+
+
+@pytest.fixture(autouse=True)
+def fp32_checker():
+    """the checker must be true fp32: no TF32 in cuDNN convolutions or cuBLAS matmuls."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def cosine(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def assert_elementwise(got, ref, rtol, what):
+    """|got - ref| <= rtol*|ref| + atol with atol tied to the tensor's own scale (values cancelling to ~0 carry the
+    accumulation-order noise of their terms, not a relative error)."""
+    ref = ref.float()
+    atol = rtol * float(ref.abs().mean()) + 1e-12
+    bad = (got.float() - ref).abs() > rtol * ref.abs() + atol
+    n_bad = int(bad.sum())
+    assert n_bad == 0, f"{what}: {n_bad} of {bad.numel()} elements off, first at {bad.nonzero()[0].tolist()}"
+
+
+def nchw(t):   # NHWC bf16 -> NCHW fp32 (a view; cuDNN takes channels_last strides)
+    return t.float().permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("hw,c0,c1,co", LAYERS)
+def test_conv3x3_fprop_dgrad_wgrad_elementwise_at_benchmark_shapes(ops, hw, c0, c1, co):
+    n, ci = 16, c0 + c1
+    g = torch.Generator(device="cuda").manual_seed(hw + ci + co)
+    x = torch.randn(n, hw, hw, ci, device="cuda", generator=g).to(bf16)
+    dy = (torch.randn(n, hw, hw, co, device="cuda", generator=g) * 0.1).to(bf16)
+    wt = (torch.randn(co, ci, 3, 3, device="cuda", generator=g) * (1.0 / (3.0 * ci ** 0.5))).to(bf16).float()
+    bias = torch.randn(co, device="cuda", generator=g) * 0.1
+    wf, wd = ops.pack_conv3x3(wt)
+    x0 = x[..., :c0].contiguous()
+    x1 = x[..., c0:].contiguous() if c1 else None
+
+    # ---- checker: stock fp32 conv + autograd on the device
+    xr = nchw(x).requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    pre = F.conv2d(xr, wr, bias, padding=1)
+    pre.backward(nchw(dy))
+    ref_y = torch.relu(pre.detach())
+
+    # ---- forward: +bias, ReLU, bf16 store, BatchNorm sum / sum of squares from the epilogue
+    s_sum = torch.zeros(co, device="cuda", dtype=torch.float64)
+    s_sq = torch.zeros(co, device="cuda", dtype=torch.float64)
+    y = ops.conv3x3_fprop(x0, x1, wf, bias, relu=True, stats=(s_sum, s_sq))
+    got = nchw(y)
+    assert rel(got, ref_y) <= BF16_TOL
+    assert_elementwise(got, ref_y, 1e-2, "fprop")
+    yd = y.double().reshape(-1, co)
+    assert torch.allclose(s_sum, yd.sum(0), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(s_sq, (yd * yd).sum(0), rtol=1e-6, atol=1e-6)
+
+    # ---- data gradient (two destinations when the input is a folded concat)
+    dx0, dx1 = ops.conv3x3_dgrad(dy, wd, c0, c1)
+    gotd = nchw(dx0) if dx1 is None else torch.cat([nchw(dx0), nchw(dx1)], 1)
+    assert rel(gotd, xr.grad) <= BF16_TOL
+    assert_elementwise(gotd, xr.grad, 1e-2, "dgrad")
+
+    # ---- weight gradient, fp32 [9][Cin][Cout] (split-K, fp32 REDs): K = 16*hw*hw terms per element
+    dw = ops.conv3x3_wgrad(dy, x0, x1)
+    gotw = dw.reshape(3, 3, ci, co).permute(3, 2, 0, 1)
+    assert rel(gotw, wr.grad) <= 1e-4
+    assert_elementwise(gotw, wr.grad, 2e-3, "wgrad")
+
+
+@pytest.mark.parametrize("hw,ci,co", [(16, 1024, 512), (32, 512, 256), (64, 256, 128), (128, 128, 64)])
+def test_conv_transpose_elementwise_at_benchmark_shapes(ops, hw, ci, co):
+    """ConvTranspose2d 2x2 / stride 2 (models/unet.py:34) at the four decoder shapes of the step."""
+    n = 16
+    g = torch.Generator(device="cuda").manual_seed(hw + ci)
+    x = torch.randn(n, hw, hw, ci, device="cuda", generator=g).to(bf16)
+    dy = (torch.randn(n, 2 * hw, 2 * hw, co, device="cuda", generator=g) * 0.1).to(bf16)
+    wt = (torch.randn(ci, co, 2, 2, device="cuda", generator=g) * (1.0 / ci ** 0.5)).to(bf16).float()
+    bias = torch.randn(co, device="cuda", generator=g) * 0.1
+    wf, wd = ops.pack_convT(wt)
+    xr = nchw(x).requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    ref = F.conv_transpose2d(xr, wr, bias, stride=2)
+    ref.backward(nchw(dy))
+    y = ops.convT_fprop(x, wf, bias)
+    assert rel(nchw(y), ref.detach()) <= BF16_TOL
+    assert_elementwise(nchw(y), ref.detach(), 1e-2, "convT fprop")
+    dx = ops.convT_dgrad(dy, wd)
+    assert rel(nchw(dx), xr.grad) <= BF16_TOL
+    assert_elementwise(nchw(dx), xr.grad, 1e-2, "convT dgrad")
+    dw = ops.convT_wgrad(x, dy)   # fp32 [4][Cin][Cout]
+    gotw = torch.empty(ci, co, 2, 2, device="cuda")
+    ops.unpack_wgrad(dw, gotw, ci, co, 4, ci, co)
+    assert rel(gotw, wr.grad) <= 1e-4
+
+
+def test_whole_step_at_16x256x256_against_fp32_on_the_device(lib_built):
+    """BASELINE config 2's exact shape: U-Net 21-class, batch 16, 256x256, structured synthetic data; the CUDA path
+    (bf16 operands, fp32 accumulate) against the oracle's functional U-Net + F.cross_entropy in fp32 on the device."""
+    import continual_learning_b200 as clk
+    from continual_learning_b200.synthetic import structured_batch
+    from oracle.unet_ref import UNetRef, clone_sd, make_state_dict, param_names
+
+    sd = make_state_dict(0)
+    x, y = structured_batch(1, 16, 256, 256)
+    x, y = x.cuda(), y.cuda()
+
+    # ---- checker (fp32, device): forward, loss, backward
+    work = clone_sd({k: v.cuda() for k, v in sd.items()}, requires_grad=True)
+    logits_ref = UNetRef(work, 21, training=True)(x)
+    loss_ref = F.cross_entropy(logits_ref, y)
+    loss_ref.backward()
+    names = param_names(sd)
+    g_ref = {k: work[k].grad for k in names}
+    logits_ref = logits_ref.detach()
+
+    # ---- the product path: drop-in module + fused loss
+    m = clk.UNet(21).cuda()
+    m.load_state_dict(sd)
+    m.train()
+    out = m(x)
+    loss = clk.CrossEntropyDistillLoss()(out, y)
+    loss.backward()
+    g = {k: p.grad for k, p in m.named_parameters()}
+
+    assert abs(float(loss) - float(loss_ref)) <= 1e-3 * float(loss_ref)
+    assert rel(out, logits_ref) <= 3e-2
+    agree = float((out.argmax(1) == logits_ref.argmax(1)).float().mean())
+    assert agree >= 0.97, agree
+    flat = torch.cat([g[k].flatten() for k in names])
+    flat_ref = torch.cat([g_ref[k].flatten() for k in names])
+    r, c = rel(flat, flat_ref), cosine(flat, flat_ref)
+    print(f"16x256x256 whole-step parity: loss {float(loss):.6f} vs {float(loss_ref):.6f}, logits rel-L2 "
+          f"{rel(out, logits_ref):.3e}, argmax agreement {agree:.4f}, global gradient rel-L2 {r:.3e} cosine {c:.6f}")
+    assert r <= 3e-2 and c >= 0.999, (r, c)
+    # per layer: every conv / convT weight gradient on its own (a wrong layer cannot hide in the global norm).
+    # Conv biases in front of a training-mode BatchNorm have a mathematically zero gradient: skipped.
+    worst = max(((rel(g[k], g_ref[k]), k) for k in names if g_ref[k].dim() == 4), key=lambda t: t[0])
+    print("worst conv weight gradient:", worst)
+    assert worst[0] <= 6e-2, worst
+    for k in names:
+        if g_ref[k].dim() == 1 and ".bias" in k and k.rsplit(".", 1)[0] + ".running_mean" in sd:   # BatchNorm beta
+            assert rel(g[k], g_ref[k]) <= 6e-2, k
+
+    # ---- the fast path bench.py times (TrainStep: fused head + loss, CUDA graph) gives the same loss
+    m2 = clk.UNet(21).cuda()
+    m2.load_state_dict(sd)
+    m2.train()
+    ts = clk.TrainStep(m2, clk.FusedAdam(m2.parameters(), lr=1e-4, betas=(0.5, 0.99)), use_graph=True)
+    l2 = float(ts.step(x, y))
+    assert abs(l2 - float(loss_ref)) <= 1e-3 * float(loss_ref)
+    g2 = torch.cat([p.grad.flatten() for p in m2.parameters()])
+    assert rel(g2, flat_ref) <= 3e-2 and cosine(g2, flat_ref) >= 0.999

@@ -57,3 +57,31 @@ def test_derived_metrics_use_reference_float32_formulas():
     assert [float(a) for a in got] == [float(b) for b in want]
     acc, tot, cor = clk.metrics.pixel_acc(torch.zeros(2, 3), None, 10.0, 4.0)
     assert (acc, tot, cor) == (100 * 4.0 / 16.0, 16.0, 4.0)
+
+
+def test_fused_adam_step_count_survives_load_state_dict():
+    """resume (trainer.py:98): the bias correction must continue from the checkpointed step, not restart at t = 1
+    on warm moments; `TrainStep` re-reads the count whenever the optimiser state is replaced."""
+    ps = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(3))]
+    ref = torch.optim.Adam(ps, lr=1e-4, betas=(0.5, 0.99))
+    for p in ps:
+        p.grad = torch.ones_like(p)
+    for _ in range(7):
+        ref.step()
+    qs = [torch.nn.Parameter(torch.zeros(4)), torch.nn.Parameter(torch.zeros(3))]
+    opt = clk.FusedAdam(qs, lr=1e-4, betas=(0.5, 0.99))
+    assert opt.group_step(qs) == 0.0 and opt.state_epoch == 0
+    opt.load_state_dict(ref.state_dict())       # the reference's optimizer_state loads into the drop-in
+    assert opt.state_epoch == 1 and opt.group_step(qs) == 7.0
+    ts = clk.TrainStep(clk.UNet(21), opt)   # host-side object only: nothing is launched
+    ts._sync_step_count()
+    assert ts.step_count == 7
+    assert opt.hyper_values(ts.step_count + 1)[1] == 1 - 0.5 ** 8
+    opt.set_group_step(qs, 9)
+    assert opt.group_step(qs) == 9.0 and opt.state[qs[0]]["step"] is opt.state[qs[1]]["step"]
+    opt.state[qs[1]]["step"] = torch.tensor(3.0)
+    try:
+        opt.group_step(qs)
+        raise AssertionError("disagreeing step counts must raise")
+    except RuntimeError:
+        pass

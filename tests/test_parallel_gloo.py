@@ -40,6 +40,11 @@ def test_shard_batch():
     assert parallel.shard_batch(x, 1, 4).flatten().tolist() == [2, 3]
     with pytest.raises(ValueError):
         parallel.shard_batch(x, 0, 3)
+    # validation batches may be ragged (no drop_last on the reference's val loader, main.py:39-41)
+    parts = [parallel.shard_batch(x, r, 3, ragged=True).flatten().tolist() for r in range(3)]
+    assert parts == [[0, 1, 2], [3, 4, 5], [6, 7]]
+    y = torch.arange(2).view(2, 1)
+    assert [parallel.shard_batch(y, r, 4, ragged=True).shape[0] for r in range(4)] == [1, 1, 0, 0]
 
 
 def _free_port():
@@ -69,6 +74,10 @@ def _worker(rank, world, port, out):
     correct = torch.tensor([10 * (rank + 1)], dtype=torch.int64)
     conf2, correct2 = parallel.all_reduce_confusion(conf, correct)
     ok = ok and bool((conf2 == 3).all()) and int(correct2) == 30 and comm.world_size == 2 and (r, w) == (rank, world)
+    # the form Trainer.test() uses (trainer.py:270-284): no matrix, two counters {correct, total}
+    _, both = parallel.all_reduce_confusion(torch.zeros(0, dtype=torch.int64),
+                                            torch.tensor([7 * (rank + 1), 100 * (rank + 1)], dtype=torch.int64))
+    ok = ok and both.tolist() == [21, 300]
     out[rank] = ok
     dist.destroy_process_group()
 
