@@ -24,6 +24,7 @@ int g_wgrad_ctas = 0;         // generic wgrad: total CTAs aimed at by the split
 int g_wgrad_bn = 64;
 int g_wgrad_v2 = 2;          // conv3x3 wgrad: 0 generic, 1 halo (1 CTA), 2 CTA-pair halo where Cout % 128 == 0 (default)
 int g_conv3_v2 = 4;          // conv3x3 fprop/dgrad kernel: 0 generic, 1 hybrid, 2 halo (1 CTA), 4 CTA-pair halo (default)
+int g_conv3_rowtap = 1;      // 64-output-channel conv3x3 forward / dgrad on the row-tap kernel (N = 192), K <= 128
 int g_conv3_pair = 1;        // CTA-pair kernel (cta_group::2, BN = 256) whenever the N extent is a multiple of 256
 int g_conv3_min_hw = 2048;  // halo kernel for images with at least this many pixels; smaller maps use the generic kernel (BN up to 256)
 int g_num_sms_api = 148;
@@ -236,6 +237,7 @@ int clk_set_tuning(const char* key, int value) {
   else if (strcmp(key, "conv3_v2") == 0) g_conv3_v2 = value;
   else if (strcmp(key, "conv3_min_hw") == 0) g_conv3_min_hw = value;
   else if (strcmp(key, "conv3_pair") == 0) g_conv3_pair = value;
+  else if (strcmp(key, "conv3_rowtap") == 0) g_conv3_rowtap = value;
   else if (strcmp(key, "pdl") == 0) g_pdl = value ? 1 : 0;
   else if (strcmp(key, "convT_wide") == 0) g_convT_wide = value ? 1 : 0;
   else if (strcmp(key, "pdl_tensor_trigger") == 0) return cuda_status(igemm_set_pdl_mode(value), "pdl_tensor_trigger");
@@ -320,6 +322,18 @@ static int conv3x3_fprop_impl(const void* x0, int C0, const void* x1, int C1, co
     q.bn_scale = bn_scale;
     q.bn_shift = bn_shift;
     CUtensorMap a0, a1, b;
+    if (pair && g_conv3_rowtap && Cout == 64 && q.kc0 + q.kc1 <= 2) {
+      // row-tap kernel: the three horizontal taps of a kernel row in one N = 192 MMA (igemm_conv3r_kernel)
+      q.tiles_w = (W + 29) / 30;
+      q.tiles_h = (H + 7) / 8;
+      q.m_tiles = N * q.tiles_h * q.tiles_w;
+      q.n_tiles = 1;
+      CHECK_RC(map_nhwc(&a0, x0, N, H, W, C0, 32, 6, 1));
+      if (x1) CHECK_RC(map_nhwc(&a1, x1, N, H, W, C1, 32, 6, 1));
+      else a1 = a0;
+      CHECK_RC(map_weights(&b, w, 3, 192, C0 + C1, 96));
+      return cuda_status(launch_conv3r(a0, a1, b, q, g_num_sms_api, S(st)), "conv3x3_fprop(row-tap)");
+    }
     int sub = BNq == 256 ? 1 : 2;
     if (pair && BNq == 256 && 2 * q.m_tiles * q.n_tiles <= g_num_sms_api / 2) {
       BNq = 128;  // fewer tiles than half the clusters: split N finer (one 16x16-pixel sub tile, 128 columns)
@@ -402,6 +416,15 @@ int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C
     q.dst1 = dx1;
     q.ldc1 = C1;
     CUtensorMap a0, b;
+    if (pair && g_conv3_rowtap && Cin2 == 64 && q.kc0 <= 2) {
+      q.tiles_w = (W + 29) / 30;
+      q.tiles_h = (H + 7) / 8;
+      q.m_tiles = N * q.tiles_h * q.tiles_w;
+      q.n_tiles = 1;
+      CHECK_RC(map_nhwc(&a0, dy, N, H, W, Cout, 32, 6, 1));
+      CHECK_RC(map_weights(&b, wd, 3, 192, Cout, 96));
+      return cuda_status(launch_conv3r(a0, a0, b, q, g_num_sms_api, S(st)), "conv3x3_dgrad(row-tap)");
+    }
     int sub = BNq == 256 ? 1 : 2;
     if (pair && BNq == 256 && 2 * q.m_tiles * q.n_tiles <= g_num_sms_api / 2) {
       BNq = 128;  // fewer tiles than half the clusters: split N finer (one 16x16-pixel sub tile, 128 columns)

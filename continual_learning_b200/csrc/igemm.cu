@@ -1494,6 +1494,275 @@ cudaError_t launch_conv3x2(int BN, int SUB, const CUtensorMap& a0, const CUtenso
 }
 
 // ------------------------------------------------------------------------------------------
+// CONV3R (conv3x3 forward / dgrad with 64 OUTPUT channels, "row-tap" formulation, CTA pairs, M = 256, N = 192).
+//   The 64-column layers at full resolution (enc1.3, last.0, last.3 and the data gradients that produce 64 channels:
+//   models/unet.py:53,66,69) are 20 % of the step's FLOPs.  In the tap-by-tap kernel above they are bound by the
+//   shared-memory operand port: every one of the nine taps re-reads the A window (128 rows x 32 B per MMA) against
+//   only 64 columns of tensor work (measured: tensor pipe 32-38 %, shared-memory port 47-55 %).  Here the three
+//   HORIZONTAL taps of a kernel row share one A window:
+//       E_s[h, w'] = sum_r sum_c X[h + r - 1, w', c] * W[o, c, r, s]        (s = 0..2, all three in ONE MMA: N = 3 x 64)
+//       out[h, w]  = E_0[h, w - 1] + E_1[h, w] + E_2[h, w + 1]
+//   so A is read 3 times instead of 9 per output and every MMA carries 192 columns.  The packed weights
+//   [tap = 3r + s][64][K] ARE the B operand [r][192][K] as they lie in memory.  The horizontal shift-and-add happens
+//   in the epilogue: a warp owns one image row segment of 32 pixels (its 32 TMEM lanes), so E_0 / E_2 come from the
+//   neighbouring lanes by warp shuffle; 30 of the 32 pixels of a segment are outputs (the outer two are halo columns).
+//   CTA r of the pair owns 4 image rows x 32 pixels (M = 128): halo tile 6 rows x 32 px x 64 ch = 24 KB per 64-channel
+//   chunk, a plain K-major SWIZZLE_128B tile; row tap r starts 32 rows (4 KB) further down: no shifted descriptors.
+//   The whole weight set (K <= 128: 72 KB per CTA pair half) stays resident in shared memory for the kernel's lifetime.
+//   BatchNorm statistics are accumulated per thread in registers across all tiles (fixed lane = fixed pixel column
+//   class) and reduced across lanes ONCE per CTA.
+constexpr int kRtTileW = 30;             // output pixels per row segment (32 lanes - 2 halo columns)
+constexpr int kRtABytes = 6 * 32 * 128;  // halo tile of one 64-channel chunk
+constexpr int kRtWBytes = 96 * 128;      // this CTA's half (96 of 192 rows) of one (chunk, row tap) weight tile
+constexpr int kRtAS = 4;                 // halo stages
+constexpr int kRtMaxKc = 2;              // 64-channel chunks of K kept resident
+constexpr int kRtSmem = kRtAS * kRtABytes + kRtMaxKc * 3 * kRtWBytes + 4 * 64 * 4 + (2 * kRtAS + 4 + 1) * 8 + 16 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
+    igemm_conv3r_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+                        const __grid_constant__ CUtensorMap mapB, const __grid_constant__ Conv3Params p) {
+  constexpr int AS = kRtAS;
+  constexpr uint32_t TMEM_COLS = 512;  // 2 accumulator stages x 192 columns, rounded up to a power of two
+
+  if (d_pdl_mode == 0) pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + AS * kRtABytes;
+  float* s_sum = reinterpret_cast<float*>(sW + kRtMaxKc * 3 * kRtWBytes);
+  float* s_sq = s_sum + 64;
+  float* s_bias = s_sq + 64;
+  float* s_aux = s_bias + 64;  // unused padding slot (keeps the barriers 8-byte aligned)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_aux + 64);
+  uint64_t* a_empty = a_full + AS;
+  uint64_t* acc_full = a_empty + AS;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* w_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int nclusters = gridDim.x >> 1;
+  const int kc = p.kc0 + p.kc1;
+  const int total = p.m_tiles;  // one N tile (64 output channels)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < AS; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 16);
+    }
+    mbar_init(w_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&mapA0);
+    tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  for (int i = threadIdx.x; i < 64; i += kC3Threads) {
+    s_sum[i] = 0.f;
+    s_sq[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------------------------ TMA producer (one per CTA)
+    if (elect_one()) {
+      // resident weights: (chunk, row tap) tiles of 96 rows (this CTA's half of the 192 columns)
+      if (leader) mbar_arrive_expect_tx(w_full, 2 * kc * 3 * kRtWBytes);
+      for (int ch = 0; ch < kc; ++ch)
+        for (int r = 0; r < 3; ++r)
+          tma_load_3d_2sm(sW + (ch * 3 + r) * kRtWBytes, &mapB, leader_bar_addr(w_full), ch * 64,
+                          static_cast<int>(rank) * 96, r);
+      uint32_t ia = 0;
+      for (int t = cluster_id; t < total; t += nclusters) {
+        const int tx = t % p.tiles_w;
+        const int rr = t / p.tiles_w;
+        const int ty = rr % p.tiles_h;
+        const int n = rr / p.tiles_h;
+        const int w0 = tx * kRtTileW - 1;
+        const int h0 = ty * 8 + 4 * static_cast<int>(rank) - 1;
+        for (int ch = 0; ch < kc; ++ch, ++ia) {
+          const uint32_t sa = ia % AS, pa = (ia / AS) & 1;
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          if (leader) mbar_arrive_expect_tx(&a_full[sa], 2 * kRtABytes);
+          if (ch < p.kc0)
+            tma_load_5d_2sm(sA + sa * kRtABytes, &mapA0, leader_bar_addr(&a_full[sa]), ch * 64, w0, h0, n, 0);
+          else
+            tma_load_5d_2sm(sA + sa * kRtABytes, &mapA1, leader_bar_addr(&a_full[sa]), (ch - p.kc0) * 64, w0, h0, n, 0);
+        }
+      }
+    }
+    __syncwarp();
+    if (d_pdl_mode == 1) pdl_launch_dependents();
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer: leader CTA only
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, 192, 0, 0);
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      const uint32_t wbase = smem_u32(sW);
+      uint32_t ia = 0, it = 0;
+      for (int t = cluster_id; t < total; t += nclusters, ++it) {
+        const uint32_t acc = it & 1, pacc = (it >> 1) & 1;
+        mbar_wait(&acc_empty[acc], pacc ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * 192;
+        for (int ch = 0; ch < kc; ++ch, ++ia) {
+          const uint32_t sa = ia % AS, pa = (ia / AS) & 1;
+          mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t abase = smem_u32(sA + sa * kRtABytes);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const uint32_t a = abase + r * (32 * 128);
+            const uint32_t b = wbase + (ch * 3 + r) * kRtWBytes;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16_2cta(d0, umma_smem_desc(a + k * 32, 16, 1024), umma_smem_desc(b + k * 32, 16, 1024), idesc,
+                             (ch | r | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2cta(&a_empty[sa]);
+        }
+        umma_commit_2cta(&acc_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------ epilogue: 8 warps; quadrant q = warp % 4 = image row of this
+    // CTA's four, `half` = which 32 of the 64 output channels
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int etid = threadIdx.x - 64;
+    const bool do_stats = p.stat_sum != nullptr;
+    const bool affine = p.bn_scale != nullptr;
+    for (int i = etid; i < 64; i += kC3EpiThreads) {
+      s_bias[i] = (p.bias != nullptr && i < p.n_store) ? p.bias[i] : 0.f;
+      if (affine) {  // inference: the statistics slots hold the BatchNorm scale / shift
+        s_sum[i] = i < p.n_store ? p.bn_scale[i] : 0.f;
+        s_sq[i] = i < p.n_store ? p.bn_shift[i] : 0.f;
+      }
+    }
+    named_bar_sync(2, kC3EpiThreads);
+    float ssum[32], ssq[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      ssum[j] = 0.f;
+      ssq[j] = 0.f;
+    }
+    uint32_t it = 0;
+    for (int t = cluster_id; t < total; t += nclusters, ++it) {
+      const int tx = t % p.tiles_w;
+      const int rr = t / p.tiles_w;
+      const int ty = rr % p.tiles_h;
+      const int n = rr / p.tiles_h;
+      const uint32_t acc = it & 1, pacc = (it >> 1) & 1;
+      const int h = ty * 8 + 4 * static_cast<int>(rank) + q;
+      const int w = tx * kRtTileW + lane - 1;
+      const bool valid = lane >= 1 && lane <= kRtTileW && h < p.H && w < p.W;
+      const long long pixoff = valid ? (static_cast<long long>(n) * p.H + h) * p.W + w : 0;
+      mbar_wait(&acc_full[acc], pacc);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 192 + half * 32;
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        uint32_t vl[16], vc[16], vr[16];
+        tmem_ld16(tbase + part * 16, vl);        // E_0: tap s = 0 multiplies X[w - 1]
+        tmem_ld16(tbase + 64 + part * 16, vc);   // E_1
+        tmem_ld16(tbase + 128 + part * 16, vr);  // E_2: tap s = 2 multiplies X[w + 1]
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          float x[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int j = 2 * jj + e;
+            const int c = half * 32 + part * 16 + j;
+            // lane l holds E_s at image column w0 - 1 + l; the output at lane l needs E_0 of lane l - 1 and E_2 of lane l + 1
+            float v = __shfl_up_sync(0xffffffffu, __uint_as_float(vl[j]), 1) + __uint_as_float(vc[j]) +
+                      __shfl_down_sync(0xffffffffu, __uint_as_float(vr[j]), 1) + s_bias[c];
+            if (p.relu) v = fmaxf(v, 0.f);
+            if (affine) v = fmaf(v, s_sum[c], s_sq[c]);
+            x[e] = v;
+          }
+          pk[jj] = pack_bf16x2(x[0], x[1]);
+        }
+        if (valid) {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dst0) + pixoff * p.ldc0 + half * 32 +
+                                              part * 16);
+          o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        if (do_stats && valid) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const float lo = bf16lo_to_f32(pk[jj]), hi = bf16hi_to_f32(pk[jj]);
+            ssum[part * 16 + 2 * jj] += lo;
+            ssum[part * 16 + 2 * jj + 1] += hi;
+            ssq[part * 16 + 2 * jj] = fmaf(lo, lo, ssq[part * 16 + 2 * jj]);
+            ssq[part * 16 + 2 * jj + 1] = fmaf(hi, hi, ssq[part * 16 + 2 * jj + 1]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
+    }
+    if (do_stats) {
+      // one cross-lane reduction per CTA: column sums of the per-thread partials, then 4 warps per channel half meet
+      // in shared memory, then ONE fp64 atomic per channel and CTA
+      const float s = warp_colsum32(ssum, lane);
+      const float sq = warp_colsum32(ssq, lane);
+      atomicAdd(&s_sum[half * 32 + lane], s);
+      atomicAdd(&s_sq[half * 32 + lane], sq);
+      named_bar_sync(1, kC3EpiThreads);
+      for (int i = etid; i < 64; i += kC3EpiThreads) {
+        if (i < p.n_store) {
+          atomicAdd(&p.stat_sum[i], static_cast<double>(s_sum[i]));
+          atomicAdd(&p.stat_sq[i], static_cast<double>(s_sq[i]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+}
+
+// a0/a1 box {64, 32, 6, 1, 1}; b = the packed weights viewed as [3][192][K], box {64, 96, 1}; p.tiles_w = ceil(W / 30),
+// p.tiles_h = ceil(H / 8), p.m_tiles = N * tiles_h * tiles_w; kc0 + kc1 <= 2; single destination, 64 columns.
+cudaError_t launch_conv3r(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const Conv3Params& p,
+                          int num_sms, cudaStream_t st) {
+  if (p.kc0 + p.kc1 > kRtMaxKc || p.split_c != 0 || p.n_store > 64) return cudaErrorInvalidValue;
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_conv3r_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRtSmem);
+    if (e != cudaSuccess) return e;
+  }
+  int clusters = p.m_tiles;
+  if (clusters > num_sms / 2) clusters = num_sms / 2;
+  launch_k(igemm_conv3r_kernel, dim3(2 * clusters), dim3(kC3Threads), kRtSmem, st, a0, a1, b, p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 template <int BN, int STAGES>
 static constexpr int fprop_smem_bytes() {

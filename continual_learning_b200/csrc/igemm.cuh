@@ -118,6 +118,9 @@ struct Conv3Params {
 // CTA-pair variant (tcgen05.mma.cta_group::2, M = 256): a0/a1 box {64, 16, 18}, b box {64, BN/2, 1}
 cudaError_t launch_conv3x2(int BN, int SUB, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const Conv3Params& p, int num_sms, cudaStream_t st);
+// row-tap variant for 64 output channels (three horizontal taps per MMA, N = 192), see igemm_conv3r_kernel
+cudaError_t launch_conv3r(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const Conv3Params& p,
+                          int num_sms, cudaStream_t st);
 cudaError_t launch_conv3(int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                          const Conv3Params& p, int num_sms, cudaStream_t st);
 

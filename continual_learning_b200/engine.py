@@ -58,7 +58,8 @@ class UNetEngine:
         self._pending = []
         self.use_side_stream = True
         # split-K weight gradients: False = fp32 vector REDs into one L2-resident buffer per layer (fastest);
-        # True = per-split partial buffers summed in a fixed order (bit-reproducible, ~0.15 ms/step slower)
+        # True = per-split partial buffers summed in a fixed order (that kernel is bit-reproducible; the STEP is not:
+        # BatchNorm statistics still use atomics) , ~0.15 ms/step slower
         self.deterministic = False
         self._forked = False
         self.fuse_bn = False     # finalize folded into the apply kernels: measured 0.17 ms/step SLOWER (fp64 prologue per block)
@@ -184,10 +185,12 @@ class UNetEngine:
         c = self.m.conv_dim
         nc = self.m.num_classes
         pack, t0 = [[], []], [0, 0]
-        unpack = [[], []]   # group 0: head + decoder (final first in backward), group 1: encoder
-        reduce_, rb0 = [[], []], [0, 0]
-        cvt = [[], []]
-        ut0 = [0, 0]
+        # gradient groups in the order the backward pass finishes them: 0 = head + decoder, 1 = enc4, 2 = enc3..enc1
+        NG = 3
+        unpack = [[] for _ in range(NG)]
+        reduce_, rb0 = [[] for _ in range(NG)], [0] * NG
+        cvt = [[] for _ in range(NG)]
+        ut0 = [0] * NG
 
         def add_pack(src, ab, ba, A, B, T, ldA, ldB, ldB2, ldA2, rev, grp=1):
             n, tb = self._tiles(A, B)
@@ -206,7 +209,7 @@ class UNetEngine:
             cvt[g].append([src.data_ptr(), dst.data_ptr(), n, 0, 1, one, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0])
 
         for i, u in enumerate(self.units):
-            g = 1 if i < 8 else 0
+            g = 0 if i >= 8 else (1 if i >= 6 else 2)
             w = u.conv.weight
             if u.stem:
                 k = self.m.in_dim * 9
@@ -234,9 +237,9 @@ class UNetEngine:
             return torch.tensor(rows, dtype=torch.int64).to(dev)
 
         self.pack_jobs = [(dev_table(pack[g]), len(pack[g]), t0[g]) for g in range(2)]
-        self.unpack_jobs = [(dev_table(unpack[g]), len(unpack[g]), ut0[g]) for g in range(2)]
-        self.cvt_jobs = [(dev_table(cvt[g]), len(cvt[g])) for g in range(2)]
-        self.reduce_jobs = [((dev_table(reduce_[g]) if reduce_[g] else None), len(reduce_[g]), rb0[g]) for g in range(2)]
+        self.unpack_jobs = [(dev_table(unpack[g]), len(unpack[g]), ut0[g]) for g in range(NG)]
+        self.cvt_jobs = [(dev_table(cvt[g]), len(cvt[g])) for g in range(NG)]
+        self.reduce_jobs = [((dev_table(reduce_[g]) if reduce_[g] else None), len(reduce_[g]), rb0[g]) for g in range(NG)]
 
     def _flush_grads(self, g):
         self._join()  # weight gradients run on the side stream
@@ -344,9 +347,18 @@ class UNetEngine:
         self.logits = ops.gemm_fprop(z, self.hwf, self.head.bias.detach(), self.m.num_classes, out_f32=True)
         return self.logits
 
-    def head_loss_backward(self, labels, loss_acc, old_logits=None, T=2.0, lam=1.0, err_flag=None, after_decoder=None):
+    def head_loss_backward(self, labels, loss_acc, old_logits=None, T=2.0, lam=1.0, err_flag=None, after_decoder=None,
+                           after_group=None):
         """after forward(head=False): 1x1 head + CrossEntropy (+ distillation) + the head's backward in one launch,
         then the rest of the backward pass.  Adds {sum CE, sum KL} to loss_acc (f64[2]); returns the gradient views."""
+        for g in self.head_loss_backward_segments(labels, loss_acc, old_logits, T, lam, err_flag):
+            self._group_done(g, after_decoder, after_group)
+        return [self.gview[p] for p in self.params]
+
+    def head_loss_backward_segments(self, labels, loss_acc, old_logits=None, T=2.0, lam=1.0, err_flag=None):
+        """generator form: yields the index of each gradient group (0 = head + decoder, 1 = enc4, 2 = enc3..enc1) as
+        soon as its gradients are final in the flat buffer `G` — a data-parallel caller all-reduces that group while
+        the rest of the backward pass runs (and may capture each segment in its own CUDA graph)."""
         U = self.units
         z = U[17].z
         self._begin_backward()
@@ -354,7 +366,14 @@ class UNetEngine:
         _, dz, _, _ = ops.head_loss_bwd(z, self.hwf, self.hwd, self.head.bias.detach(), labels, self.m.num_classes,
                                         old_logits=old_logits, T=T, lam=lam, gscale=1.0 / (n * h * w), dw=self.hgp,
                                         dbias=self.hdbias, loss_acc=loss_acc, err_flag=err_flag)
-        return self.backward(None, after_decoder=after_decoder, dz_head=dz)
+        yield from self.backward_segments(None, dz_head=dz)
+
+    @staticmethod
+    def _group_done(g, after_decoder, after_group):
+        if g == 0 and after_decoder is not None:
+            after_decoder()
+        if after_group is not None:
+            after_group(g)
 
     # ------------------------------------------------------------------ backward
     def _unit_bwd(self, u, dz, need_dx=True):
@@ -435,12 +454,31 @@ class UNetEngine:
         self.acc_b.zero_()
         self.Gp.zero_()
 
-    def backward(self, dlogits, after_decoder=None, dz_head=None):
+    def backward(self, dlogits, after_decoder=None, dz_head=None, after_group=None):
         """dlogits: bf16 [N, H, W, 64] (columns >= num_classes zero). Fills the flat gradient buffer and
         returns the per-parameter gradient views (PyTorch layouts) in `module.parameters()` order.
-        `after_decoder()` is called once the head + decoder gradients are final (85 % of the bytes), so a
-        data-parallel caller can start reducing them while the encoder backward still runs.
+        `after_decoder()` is called once the head + decoder gradients are final (85 % of the bytes), `after_group(g)`
+        after each of the three gradient groups, so a data-parallel caller can start reducing them while the rest
+        of the backward pass still runs.
         dz_head: the head's input gradient when `head_loss_backward` already did the head (dlogits is then None)."""
+        for g in self.backward_segments(dlogits, dz_head=dz_head):
+            self._group_done(g, after_decoder, after_group)
+        return [self.gview[p] for p in self.params]
+
+    # parameters() order is enc1..enc4, dec1..dec4, last: the three gradient groups as [first, last) unit indices
+    GROUP_NAMES = ("head+decoder", "enc4", "enc3..enc1")
+
+    def group_param_ranges(self):
+        """[(start, end)] element ranges of the three gradient groups inside the flat buffer `G`."""
+        names = [k for k, _ in self.m.named_parameters()]
+        offs = [0]
+        for p in self.m.parameters():
+            offs.append(offs[-1] + p.numel())
+        first_dec = next(i for i, nm in enumerate(names) if nm.startswith("dec"))
+        first_enc4 = next(i for i, nm in enumerate(names) if nm.startswith("enc4"))
+        return [(offs[first_dec], offs[-1]), (offs[first_enc4], offs[first_dec]), (0, offs[first_enc4])]
+
+    def backward_segments(self, dlogits, dz_head=None):
         U = self.units
         if dz_head is None:
             self._begin_backward()
@@ -465,15 +503,17 @@ class UNetEngine:
             else:
                 dpool = dskip  # gradient of the centre pool output
         self._flush_grads(0)  # head + decoder gradients -> PyTorch layout (one batched launch each)
-        if after_decoder is not None:
-            after_decoder()
+        yield 0
         # encoder, deepest first: enc4 (U[7]) .. enc1 (U[1])
         for lvl, k in ((3, 7), (2, 5), (1, 3), (0, 1)):
             dz = ops.maxpool_bwd_add(dpool, U[k].idx, skip_grads[lvl])
             dz, _ = self._unit_bwd(U[k], dz)
             dpool, _ = self._unit_bwd(U[k - 1], dz, need_dx=(k > 1))
-        self._flush_grads(1)  # encoder gradients
-        return [self.gview[p] for p in self.params]
+            if k == 7:
+                self._flush_grads(1)  # enc4: 11 % of the parameters, final long before the backward pass ends
+                yield 1
+        self._flush_grads(2)  # enc3..enc1
+        yield 2
 
     def release(self):
         """drop the saved activations (after backward, or after an eval forward)."""

@@ -21,9 +21,11 @@ class TrainStep:
             raise TypeError("TrainStep needs continual_learning_b200.FusedAdam")
         self.model, self.opt, self.old = model, optimizer, old_model
         self.T, self.lam = float(T), float(lam)
-        # with a communicator the step runs eagerly: capturing the NCCL all-reduces into the graph hung (twice, global and thread_local capture modes) on
-        # B200 x2 (torch 2.11 / NCCL 2.28.9), and the eager step is GPU-bound anyway (7.28 vs 7.0 ms at N=2 vs 1)
-        self.use_graph = use_graph and comm is None
+        # with a communicator the step is captured as FOUR graphs cut where a gradient group becomes final
+        # (head + decoder | enc4 | enc3..enc1 | Adam); the NCCL all-reduces are launched eagerly between the replays on
+        # NCCL's own stream and overlap the next segment (capturing the collectives themselves into one graph hung
+        # on B200 x2 with torch 2.11 / NCCL 2.28.9).  CLK_DDP_GRAPH=0 falls back to eager launches.
+        self.use_graph = use_graph and (comm is None or os.environ.get("CLK_DDP_GRAPH", "1") != "0")
         # head GEMM + loss + head backward as one kernel (needs the reference geometry: 64 channels, <= 32 classes)
         self.fused_head = (model.conv_dim == 64 and model.num_classes <= 32
                            and os.environ.get("CLK_FUSED_HEAD", "1") != "0")
@@ -37,22 +39,22 @@ class TrainStep:
         self._opt_ready = False
 
     # ------------------------------------------------------------------ one eager step on device tensors
-    def _body(self, x, y):
+    def _segments(self, x, y):
+        """the step up to the optimiser as a generator: yields the index of each gradient group (UNetEngine
+        .backward_segments) when it is final in the flat buffer, so that the caller can all-reduce it (and, in graph
+        mode, cut the CUDA graph there)."""
         eng = self.model.engine
         old_logits = None
         if self.old is not None:
             oeng = self.old.engine
             old_logits = oeng.forward(x, training=False, save_for_backward=False)
             oeng.release()
-        hook = None
-        if self.comm is not None:
-            hook = lambda: self.comm.start_decoder(eng.G)
         if self.fused_head:
             # the logits never reach HBM: head GEMM, loss and the head's backward are one kernel
             eng.forward(x, training=self.model.training, head=False)
             self.loss_acc.zero_()
-            views = eng.head_loss_backward(y, self.loss_acc, old_logits=old_logits, T=self.T, lam=self.lam,
-                                           err_flag=self.err_flag, after_decoder=hook)
+            yield from eng.head_loss_backward_segments(y, self.loss_acc, old_logits=old_logits, T=self.T, lam=self.lam,
+                                                       err_flag=self.err_flag)
         else:
             logits = eng.forward(x, training=self.model.training)
             self.loss_acc.zero_()
@@ -61,16 +63,25 @@ class TrainStep:
                 self.dlogits = torch.zeros((n, h, w, 64), device=x.device, dtype=torch.bfloat16)
             ops.ce_kd_loss(logits, y, old_logits, T=self.T, lam=self.lam, dlogits=self.dlogits, loss_acc=self.loss_acc,
                            err_flag=self.err_flag)
-            views = eng.backward(self.dlogits, after_decoder=hook)
+            yield from eng.backward_segments(self.dlogits)
         eng.release()
-        for p, v in zip(eng.params, views):
+        for p in eng.params:
+            v = eng.gview[p]
             if p.grad is not v:  # first step, or the module was moved (.cpu()/.cuda() in save_network)
                 p.grad = v
-        gscale = 1.0
+
+    def _adam(self):
+        gscale = 1.0 if self.comm is None else 1.0 / self.comm.world_size
+        self.opt.step(grad_scale=gscale, hyper_dev=self.hyper)
+
+    def _body(self, x, y):
+        eng = self.model.engine
+        for g in self._segments(x, y):
+            if self.comm is not None:
+                self.comm.launch_group(eng.G, g)   # overlaps the rest of the backward pass
         if self.comm is not None:
             self.comm.finish(eng.G)
-            gscale = 1.0 / self.comm.world_size
-        self.opt.step(grad_scale=gscale, hyper_dev=self.hyper)
+        self._adam()
 
     def _alloc(self, x, y):
         dev = x.device
@@ -128,16 +139,43 @@ class TrainStep:
                 self.model.engine._wver = None
                 if self.old is not None:
                     self.old.engine._wver = None
-                g = torch.cuda.CUDAGraph()
                 from . import _lib
                 n0 = _lib.launch_count
-                with torch.cuda.graph(g):
-                    self._body(self.x_static, self.y_static)
-                self.launches_per_step = _lib.launch_count - n0  # clk_* kernels replayed per graph launch
-                self.graph = g
+                if self.comm is None:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._body(self.x_static, self.y_static)
+                    self.graph = [g]
+                else:
+                    # one graph per gradient group + one for Adam, sharing a memory pool (replayed in capture order)
+                    graphs, pool = [], None
+                    gen = self._segments(self.x_static, self.y_static)
+                    for _ in range(3):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, pool=pool):
+                            grp = next(gen)
+                        assert grp == len(graphs)
+                        pool = g.pool()
+                        graphs.append(g)
+                    for _ in gen:          # host-only tail of the step body (no launches)
+                        raise RuntimeError("unexpected extra gradient group")
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, pool=pool):
+                        self._adam()
+                    graphs.append(g)
+                    self.graph = graphs
+                self.launches_per_step = _lib.launch_count - n0  # clk_* kernels replayed per step
                 self._graph_ptr = self.model.engine.params[0].data_ptr()
                 self._restore(state)
-            self.graph.replay()
+            if self.comm is None:
+                self.graph[0].replay()
+            else:
+                G = self.model.engine.G
+                for grp in range(3):
+                    self.graph[grp].replay()
+                    self.comm.launch_group(G, grp)   # NCCL stream: overlaps the next segment's replay
+                self.comm.finish(G)
+                self.graph[3].replay()
         self.step_count += 1
         self.opt.set_group_step(self.model.engine.params, self.step_count)
         loss = self.loss_acc[0] / self.npix

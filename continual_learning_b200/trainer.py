@@ -194,6 +194,7 @@ class Trainer:
     def test(self):
         """pixel accuracy over the validation loader; like the reference, the model is left in eval mode."""
         self.model.eval()
+        parallel.broadcast_buffers(self.model)  # every rank evaluates with rank 0's running statistics
         correct = torch.zeros(1, device=self.device, dtype=torch.int64)
         total = 0
         with torch.no_grad():

@@ -64,7 +64,7 @@ class _UNetFn(torch.autograd.Function):
             dl = torch.zeros((*g.shape[:3], 64), device=g.device, dtype=torch.bfloat16)
             dl[..., :g.shape[3]] = g
         comm = getattr(eng, "comm", None)
-        views = eng.backward(dl, after_decoder=(lambda: comm.start_decoder(eng.G)) if comm is not None else None)
+        views = eng.backward(dl, after_group=(lambda g: comm.launch_group(eng.G, g)) if comm is not None else None)
         if comm is not None:
             comm.finish(eng.G)
         grads = []

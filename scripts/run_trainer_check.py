@@ -37,12 +37,17 @@ def main():
     tr = Trainer(train_data_loader=train_loader, val_data_loader=val_loader, config=cfg)
     tr.train_val()
     acc = tr.test()                       # 44 images in batches of 3: the last batch holds 2 (ragged at world 2)
-    # the same sweep unsharded on every rank: integer counts, so the sharded result must be identical
+    # the same sweep with EVERY shard evaluated locally (same sub-batch shapes, hence the same kernel instantiations
+    # and bit-identical predictions): integer counts, so the all-reduced result of the sharded run must be identical
     correct = torch.zeros(1, device=tr.device, dtype=torch.int64)
     total = 0
     with torch.no_grad():
         for images, labels in val_loader:
-            tr.model.evaluate_batch(images.to(tr.device), labels.to(tr.device), correct=correct)
+            for r in range(tr.world):
+                xi = parallel.shard_batch(images, r, tr.world, ragged=True)
+                yi = parallel.shard_batch(labels, r, tr.world, ragged=True)
+                if xi.shape[0]:
+                    tr.model.evaluate_batch(xi.to(tr.device), yi.to(tr.device), correct=correct)
             total += labels.nelement()
     expected = 100 * float(correct) / float(total)
     if tr.world > 1:

@@ -163,23 +163,29 @@ def test_trainstep_eager_equals_graph_and_tracks_reference_trajectory(clk, golde
     assert rel(st["last.6.weight"], torch.from_numpy(g["w_head"])) <= 2e-2
 
 
-def test_deterministic_mode_is_bit_reproducible(clk):
-    """engine.deterministic = True: split-K partial buffers + fixed-order sums instead of fp32 atomics for the
-    conv weight gradients (the remaining atomics accumulate fp64 statistics of fp32-exact partials)."""
+def test_deterministic_wgrad_mode_matches_the_red_path_to_summation_order(clk):
+    """engine.deterministic = True: split-K partial buffers + fixed-order sums instead of fp32 REDs for the conv
+    weight gradients.  The split kernel itself IS bit-reproducible on fixed inputs (asserted with torch.equal in
+    test_gpu_kernels.py::_check_conv3x3_wgrad_split); the whole step is NOT, in either mode: the BatchNorm
+    statistics of the conv epilogues and the BatchNorm-backward sums are accumulated with shared-memory / fp64
+    atomics whose order varies from run to run (measured: every gradient differs in its last bits between two runs,
+    scripts/dev_repro.py).  What holds, and is asserted here: two runs and the two modes agree to the noise of the
+    fp32 summation order."""
     sd = make_state_dict(2)
     x, y = structured_batch(3, 4, 128, 128)
+
+    def conv_grads(m):
+        return torch.cat([p.grad.flatten() for n_, p in m.named_parameters() if n_.endswith("weight") and p.dim() == 4
+                          and p.shape[-1] == 3])
     grads = []
     for _ in range(2):
         m = make_model(clk, sd)
         m.engine.deterministic = True
         clk.CrossEntropyDistillLoss()(m(x.cuda()), y.cuda()).backward()
-        grads.append(torch.cat([p.grad.flatten() for n_, p in m.named_parameters() if n_.endswith("weight") and p.dim() == 4
-                                and p.shape[-1] == 3]))
+        grads.append(conv_grads(m))
     m = make_model(clk, sd)
     clk.CrossEntropyDistillLoss()(m(x.cuda()), y.cuda()).backward()
-    fast = torch.cat([p.grad.flatten() for n_, p in m.named_parameters() if n_.endswith("weight") and p.dim() == 4
-                      and p.shape[-1] == 3])
-    # same numbers as the RED path and as a second run, up to the fp32 summation order of the BatchNorm statistics
+    fast = conv_grads(m)
     assert rel(grads[0], fast) <= 2e-2
     assert rel(grads[0], grads[1]) <= 2e-2
 

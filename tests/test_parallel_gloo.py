@@ -21,18 +21,24 @@ def _names_numels():
 
 def test_bucket_bounds_cover_the_flat_buffer_in_backward_order():
     names, numels = _names_numels()
-    bounds = parallel.bucket_bounds(numels, names, n_buckets=4)
+    groups = parallel.bucket_bounds(numels, names, n_buckets=4)
+    bounds = [b for g in groups for b in g]
     total = sum(numels)
     # disjoint, complete
     spans = sorted(bounds)
     assert spans[0][0] == 0 and spans[-1][1] == total
     for (a0, b0), (a1, b1) in zip(spans, spans[1:]):
         assert b0 == a1
-    # launch order: head/decoder buckets first (their gradients are final first), encoder last
+    # three groups in the order the backward pass finishes them: head + decoder (3 buckets, tail of the parameter
+    # list first), enc4, enc3..enc1
     enc_end = sum(n for k, n in zip(names, numels) if k.startswith("enc"))
-    assert bounds[-1] == (0, enc_end)
-    assert bounds[0][1] == total
-    assert all(bounds[i][0] >= bounds[i + 1][0] for i in range(len(bounds) - 2))
+    enc4_start = sum(n for k, n in zip(names, numels) if k.startswith(("enc1", "enc2", "enc3")))
+    assert len(groups) == 3 and len(groups[0]) == 3
+    assert groups[1] == [(enc4_start, enc_end)] and groups[2] == [(0, enc4_start)]
+    assert groups[0][0][1] == total and groups[0][-1][0] == enc_end
+    assert all(groups[0][i][0] >= groups[0][i + 1][0] for i in range(2))
+    # the exposed tail (the group that can only start after the whole backward pass) is < 5 % of the bytes
+    assert enc4_start / total < 0.05
 
 
 def test_shard_batch():
@@ -65,10 +71,10 @@ def _worker(rank, world, port, out):
     flat[::1000] += torch.arange(flat[::1000].numel(), dtype=torch.float32) * (rank + 1)
     expect = torch.full_like(flat, 3.0)
     expect[::1000] += torch.arange(flat[::1000].numel(), dtype=torch.float32) * 3
-    comm.start_decoder(flat)   # head + decoder buckets while "the encoder backward still runs"
-    enc_end = comm.bounds[-1][1]
-    flat[:enc_end] *= 1.0      # encoder gradients become final
-    comm.finish(flat)
+    comm.launch_group(flat, 0)   # head + decoder buckets while "the encoder backward still runs"
+    comm.launch_group(flat, 1)   # enc4
+    comm.launch_group(flat, 1)   # launching a group twice in one step must not reduce it twice
+    comm.finish(flat)            # launches enc3..enc1, waits for everything
     ok = torch.equal(flat, expect)
     conf = torch.full((21, 21), rank + 1, dtype=torch.int64)
     correct = torch.tensor([10 * (rank + 1)], dtype=torch.int64)
