@@ -13,7 +13,7 @@ LIB = os.path.join(HERE, "libclk.so")
 SOURCES = ["api.cu", "igemm.cu", "membound.cu"]
 HEADERS = ["clk_ptx.cuh", "igemm.cuh", "membound.cuh", os.path.join("..", "..", "include", "clk.h")]
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", *os.environ.get("CLK_NVCC_EXTRA", "").split(),
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
 ]
 

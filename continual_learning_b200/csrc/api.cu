@@ -331,8 +331,10 @@ static int conv3x3_fprop_impl(const void* x0, int C0, const void* x1, int C1, co
       CHECK_RC(map_nhwc(&a0, x0, N, H, W, C0, 32, 6, 1));
       if (x1) CHECK_RC(map_nhwc(&a1, x1, N, H, W, C1, 32, 6, 1));
       else a1 = a0;
-      CHECK_RC(map_weights(&b, w, 3, 192, C0 + C1, 96));
-      return cuda_status(launch_conv3r(a0, a1, b, q, g_num_sms_api, S(st)), "conv3x3_fprop(row-tap)");
+      CHECK_RC(map_weights(&b, w, 3, 192, C0 + C1, 32));
+      CUtensorMap o;
+      CHECK_RC(map_nhwc(&o, y, N, H, W, 64, 30, 4, 1));
+      return cuda_status(launch_conv3r(a0, a1, b, o, q, g_num_sms_api, S(st)), "conv3x3_fprop(row-tap)");
     }
     int sub = BNq == 256 ? 1 : 2;
     if (pair && BNq == 256 && 2 * q.m_tiles * q.n_tiles <= g_num_sms_api / 2) {
@@ -422,8 +424,10 @@ int clk_conv3x3_dgrad(const void* dy, int Cout, const void* wd, void* dx0, int C
       q.m_tiles = N * q.tiles_h * q.tiles_w;
       q.n_tiles = 1;
       CHECK_RC(map_nhwc(&a0, dy, N, H, W, Cout, 32, 6, 1));
-      CHECK_RC(map_weights(&b, wd, 3, 192, Cout, 96));
-      return cuda_status(launch_conv3r(a0, a0, b, q, g_num_sms_api, S(st)), "conv3x3_dgrad(row-tap)");
+      CHECK_RC(map_weights(&b, wd, 3, 192, Cout, 32));
+      CUtensorMap o;
+      CHECK_RC(map_nhwc(&o, dx0, N, H, W, 64, 30, 4, 1));
+      return cuda_status(launch_conv3r(a0, a0, b, o, q, g_num_sms_api, S(st)), "conv3x3_dgrad(row-tap)");
     }
     int sub = BNq == 256 ? 1 : 2;
     if (pair && BNq == 256 && 2 * q.m_tiles * q.n_tiles <= g_num_sms_api / 2) {

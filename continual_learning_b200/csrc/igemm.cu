@@ -1494,50 +1494,64 @@ cudaError_t launch_conv3x2(int BN, int SUB, const CUtensorMap& a0, const CUtenso
 }
 
 // ------------------------------------------------------------------------------------------
-// CONV3R (conv3x3 forward / dgrad with 64 OUTPUT channels, "row-tap" formulation, CTA pairs, M = 256, N = 192).
+// CONV3R (conv3x3 forward / dgrad with 64 OUTPUT channels, "paired-tap" formulation, CTA pairs, M = 256).
 //   The 64-column layers at full resolution (enc1.3, last.0, last.3 and the data gradients that produce 64 channels:
-//   models/unet.py:53,66,69) are 20 % of the step's FLOPs.  In the tap-by-tap kernel above they are bound by the
-//   shared-memory operand port: every one of the nine taps re-reads the A window (128 rows x 32 B per MMA) against
-//   only 64 columns of tensor work (measured: tensor pipe 32-38 %, shared-memory port 47-55 %).  Here the three
-//   HORIZONTAL taps of a kernel row share one A window:
-//       E_s[h, w'] = sum_r sum_c X[h + r - 1, w', c] * W[o, c, r, s]        (s = 0..2, all three in ONE MMA: N = 3 x 64)
-//       out[h, w]  = E_0[h, w - 1] + E_1[h, w] + E_2[h, w + 1]
-//   so A is read 3 times instead of 9 per output and every MMA carries 192 columns.  The packed weights
-//   [tap = 3r + s][64][K] ARE the B operand [r][192][K] as they lie in memory.  The horizontal shift-and-add happens
-//   in the epilogue: a warp owns one image row segment of 32 pixels (its 32 TMEM lanes), so E_0 / E_2 come from the
-//   neighbouring lanes by warp shuffle; 30 of the 32 pixels of a segment are outputs (the outer two are halo columns).
-//   CTA r of the pair owns 4 image rows x 32 pixels (M = 128): halo tile 6 rows x 32 px x 64 ch = 24 KB per 64-channel
-//   chunk, a plain K-major SWIZZLE_128B tile; row tap r starts 32 rows (4 KB) further down: no shifted descriptors.
-//   The whole weight set (K <= 128: 72 KB per CTA pair half) stays resident in shared memory for the kernel's lifetime.
-//   BatchNorm statistics are accumulated per thread in registers across all tiles (fixed lane = fixed pixel column
-//   class) and reduced across lanes ONCE per CTA.
-constexpr int kRtTileW = 30;             // output pixels per row segment (32 lanes - 2 halo columns)
+//   models/unet.py:53,66,69) are 20 % of the step's FLOPs.  In the tap-by-tap kernel above every one of the nine taps
+//   re-reads its A window (128 rows x 32 B per MMA) against only 64 columns of tensor work: 180 KB of operand reads
+//   per 128 x 64 output tile against 1152 clk of MMA, i.e. bound by the 128 B/clk shared-memory operand port
+//   (measured: tensor pipe 32-38 %, shared-memory port 47-55 %), and it pays eleven barrier hand-shakes per tile.
+//   Here two horizontal taps of a kernel row share ONE A window in ONE N = 128 MMA:
+//       G0[h, w'] += X[h + r - 1, w'] * W[r, s=0]      (columns   0..63:  belongs to output column w' + 1)
+//       G1[h, w'] += X[h + r - 1, w'] * W[r, s=1]      (columns 64..127:  belongs to output column w')
+//   and the third tap is an N = 64 MMA on the window shifted by one pixel (+128 B: the swizzle is a function of the
+//   absolute shared-memory address, scripts/desc_probe.cu), accumulating into G1:
+//       G1[h, w'] += X[h + r - 1, w' + 1] * W[r, s=2]
+//       out[h, w]  = G1[h, w] + G0[h, w - 1]
+//   Per 128 x 64 tile: the same 1152 clk of MMA (3 rows x 4 k-steps x (64 + 32) clk), 132 KB of operand reads
+//   (1031 clk of port time), 64 KB of TMEM reads (a three-column-group variant, N = 192, was measured first: its 96 KB
+//   of accumulator reads per tile made the epilogue, not the tensor pipe, set the pace).  [W(r,0); W(r,1)] are adjacent
+//   in the packed weights [tap = 3r + s][64][K], so they ARE the N = 128 B operand as they lie in memory.  The shift-and-
+//   add G0[w - 1] happens in the epilogue: a warp owns one image-row segment of 32 pixels (its 32 TMEM lanes), so the
+//   left neighbour comes by ONE warp shuffle; lanes 1..30 are outputs (lane 0 has no left neighbour, lane 31's shifted
+//   window wraps into the next image row).  CTA r of the pair owns 4 image rows x 32 pixels (M = 128): halo tile 6 rows
+//   x 32 px x 64 ch = 24 KB per 64-channel chunk, a plain K-major SWIZZLE_128B tile; kernel row r starts 32 rows (4 KB)
+//   further down.  The whole weight set (K <= 128) stays resident in shared memory; four 128-column accumulator stages
+//   decouple the MMA thread from the epilogue; BatchNorm statistics are accumulated per thread in registers across all
+//   tiles and reduced across lanes ONCE per CTA.
+constexpr int kRtTileW = 30;             // output pixels per row segment (lanes 1..30 of 32)
 constexpr int kRtABytes = 6 * 32 * 128;  // halo tile of one 64-channel chunk
-constexpr int kRtWBytes = 96 * 128;      // this CTA's half (96 of 192 rows) of one (chunk, row tap) weight tile
+constexpr int kRtWBytes = 96 * 128;      // this CTA's share of one (chunk, kernel row) weight tile: 64 + 32 rows
 constexpr int kRtAS = 4;                 // halo stages
+constexpr int kRtOBytes = 4 * 30 * 128;  // output staging tile: 4 image rows x 30 pixels x 64 channels (TMA store)
+constexpr int kRtAcc = 4;                // accumulator stages (128 TMEM columns each)
 constexpr int kRtMaxKc = 2;              // 64-channel chunks of K kept resident
-constexpr int kRtSmem = kRtAS * kRtABytes + kRtMaxKc * 3 * kRtWBytes + 4 * 64 * 4 + (2 * kRtAS + 4 + 1) * 8 + 16 + 1024;
+constexpr int kRtEpiThreads = 512;       // two groups of 8 epilogue warps, alternating tiles
+constexpr int kRtThreads = 64 + kRtEpiThreads;
+constexpr int kRtSmem = kRtAS * kRtABytes + kRtMaxKc * 3 * kRtWBytes + 2 * 16384 + 4 * 64 * 4 + (2 * kRtAS + 2 * kRtAcc + 1) * 8 + 16 + 1024;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kRtThreads, 1)
     igemm_conv3r_kernel(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
-                        const __grid_constant__ CUtensorMap mapB, const __grid_constant__ Conv3Params p) {
+                        const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
+                        const __grid_constant__ Conv3Params p) {
   constexpr int AS = kRtAS;
-  constexpr uint32_t TMEM_COLS = 512;  // 2 accumulator stages x 192 columns, rounded up to a power of two
+  constexpr int NACC = kRtAcc;
+  constexpr uint32_t TMEM_COLS = 512;  // 4 accumulator stages x 128 columns
 
   if (d_pdl_mode == 0) pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sA = smem;
   uint8_t* sW = smem + AS * kRtABytes;
-  float* s_sum = reinterpret_cast<float*>(sW + kRtMaxKc * 3 * kRtWBytes);
+  uint8_t* sO = sW + kRtMaxKc * 3 * kRtWBytes;  // two 1024-aligned output staging tiles
+  float* s_sum = reinterpret_cast<float*>(sO + 2 * 16384);
   float* s_sq = s_sum + 64;
   float* s_bias = s_sq + 64;
-  float* s_aux = s_bias + 64;  // unused padding slot (keeps the barriers 8-byte aligned)
+  float* s_aux = s_bias + 64;  // padding slot (keeps the barriers 8-byte aligned)
   uint64_t* a_full = reinterpret_cast<uint64_t*>(s_aux + 64);
   uint64_t* a_empty = a_full + AS;
   uint64_t* acc_full = a_empty + AS;
-  uint64_t* acc_empty = acc_full + 2;
-  uint64_t* w_full = acc_empty + 2;
+  uint64_t* acc_empty = acc_full + NACC;
+  uint64_t* w_full = acc_empty + NACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -1554,7 +1568,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
       mbar_init(&a_full[s], 1);
       mbar_init(&a_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NACC; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 16);
     }
@@ -1563,12 +1577,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
     tma_prefetch_desc(&mapA0);
     tma_prefetch_desc(&mapA1);
     tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&mapO);
   }
   if (warp == 1) {
     tmem_alloc_2cta(tmem_slot, TMEM_COLS);
     tmem_relinquish_2cta();
   }
-  for (int i = threadIdx.x; i < 64; i += kC3Threads) {
+  for (int i = threadIdx.x; i < 64; i += kRtThreads) {
     s_sum[i] = 0.f;
     s_sq[i] = 0.f;
   }
@@ -1582,12 +1597,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
   if (warp == 0) {
     // ------------------------------------------------ TMA producer (one per CTA)
     if (elect_one()) {
-      // resident weights: (chunk, row tap) tiles of 96 rows (this CTA's half of the 192 columns)
+      // resident weights, per (chunk, kernel row): rows [0, 64) = this CTA's half of the N = 128 operand
+      // [W(r,0); W(r,1)] (CTA 0 holds W(r,0), CTA 1 holds W(r,1)), rows [64, 96) = its half of W(r,2); three 32-row boxes
       if (leader) mbar_arrive_expect_tx(w_full, 2 * kc * 3 * kRtWBytes);
       for (int ch = 0; ch < kc; ++ch)
-        for (int r = 0; r < 3; ++r)
-          tma_load_3d_2sm(sW + (ch * 3 + r) * kRtWBytes, &mapB, leader_bar_addr(w_full), ch * 64,
-                          static_cast<int>(rank) * 96, r);
+        for (int r = 0; r < 3; ++r) {
+          uint8_t* dst = sW + (ch * 3 + r) * kRtWBytes;
+          const int row0 = static_cast<int>(rank) * 64;
+          tma_load_3d_2sm(dst, &mapB, leader_bar_addr(w_full), ch * 64, row0, r);
+          tma_load_3d_2sm(dst + 32 * 128, &mapB, leader_bar_addr(w_full), ch * 64, row0 + 32, r);
+          tma_load_3d_2sm(dst + 64 * 128, &mapB, leader_bar_addr(w_full), ch * 64, 128 + static_cast<int>(rank) * 32, r);
+        }
       uint32_t ia = 0;
       for (int t = cluster_id; t < total; t += nclusters) {
         const int tx = t % p.tiles_w;
@@ -1612,29 +1632,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
   } else if (warp == 1) {
     // ------------------------------------------------ MMA issuer: leader CTA only
     if (leader && elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(256, 192, 0, 0);
+      constexpr uint32_t idesc128 = umma_idesc_bf16(256, 128, 0, 0);
+      constexpr uint32_t idesc64 = umma_idesc_bf16(256, 64, 0, 0);
       mbar_wait(w_full, 0);
       tc_fence_after();
       const uint32_t wbase = smem_u32(sW);
       uint32_t ia = 0, it = 0;
       for (int t = cluster_id; t < total; t += nclusters, ++it) {
-        const uint32_t acc = it & 1, pacc = (it >> 1) & 1;
+        const uint32_t acc = it % NACC, pacc = (it / NACC) & 1;
         mbar_wait(&acc_empty[acc], pacc ^ 1);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * 192;
+        const uint32_t d0 = tmem_base + acc * 128;
         for (int ch = 0; ch < kc; ++ch, ++ia) {
           const uint32_t sa = ia % AS, pa = (ia / AS) & 1;
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
           const uint32_t abase = smem_u32(sA + sa * kRtABytes);
+          // descriptors differ from one MMA to the next only by a compile-time constant in the 14-bit start-address
+          // field (all operand tiles lie below 256 KB, so the add never carries out of the field): ONE 64-bit add per
+          // descriptor keeps the single issuing thread ahead of the tensor pipe (24 MMAs of 64 / 32 clk per chunk)
+          const uint64_t adesc = umma_smem_desc(abase, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc(wbase + ch * 3 * kRtWBytes, 16, 1024);
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
-            const uint32_t a = abase + r * (32 * 128);
-            const uint32_t b = wbase + (ch * 3 + r) * kRtWBytes;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16_2cta(d0, umma_smem_desc(a + k * 32, 16, 1024), umma_smem_desc(b + k * 32, 16, 1024), idesc,
-                             (ch | r | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t ao = static_cast<uint64_t>((r * 32 * 128 + k * 32) >> 4);
+              const uint64_t bo = static_cast<uint64_t>((r * kRtWBytes + k * 32) >> 4);
+              // taps s = 0 | s = 1 on the unshifted window -> G0 | G1
+              umma_bf16_2cta(d0, adesc + ao, bdesc + bo, idesc128, (ch | r | k) != 0 ? 1u : 0u);
+              // tap s = 2 on the window shifted by one pixel (one 128-byte row) -> G1 (always accumulates: the
+              // N = 128 MMA in front of it has initialised the columns)
+              umma_bf16_2cta(d0 + 64, adesc + ao + (128 >> 4), bdesc + bo + ((64 * 128) >> 4), idesc64, 1u);
+            }
           }
           umma_commit_2cta(&a_empty[sa]);
         }
@@ -1643,95 +1673,137 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------ epilogue: 8 warps; quadrant q = warp % 4 = image row of this
-    // CTA's four, `half` = which 32 of the 64 output channels
+    // ------------------------------------------------ epilogue: 16 warps in two groups that take alternate tiles
+    // (group g owns accumulator stages g and g + 2), so each warp has two tile periods for one tile; inside a group
+    // quadrant q = warp % 4 = image row of this CTA's four, `half` = which 32 of the 64 output channels
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int etid = threadIdx.x - 64;
+    const int grp = (warp - 2) >> 3;
+    const int half = ((warp - 2) >> 2) & 1;
+    const int etid = threadIdx.x - 64;       // 0..511
+    const int gtid = etid & 255;             // thread index inside the group
     const bool do_stats = p.stat_sum != nullptr;
     const bool affine = p.bn_scale != nullptr;
-    for (int i = etid; i < 64; i += kC3EpiThreads) {
+    for (int i = etid; i < 64; i += kRtEpiThreads) {
       s_bias[i] = (p.bias != nullptr && i < p.n_store) ? p.bias[i] : 0.f;
       if (affine) {  // inference: the statistics slots hold the BatchNorm scale / shift
         s_sum[i] = i < p.n_store ? p.bn_scale[i] : 0.f;
         s_sq[i] = i < p.n_store ? p.bn_shift[i] : 0.f;
       }
     }
-    named_bar_sync(2, kC3EpiThreads);
-    float ssum[32], ssq[32];
+    named_bar_sync(1, kRtEpiThreads);
+    // BatchNorm statistics: thread e of a group sums one 16-byte chunk column (8 channels) of the STAGED bf16 tile over
+    // the rows e / 8 + 32 i — 16 accumulators per thread instead of 64, and exactly the values that were stored
+    float st_s[8], st_q[8];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      ssum[j] = 0.f;
-      ssq[j] = 0.f;
+    for (int j = 0; j < 8; ++j) {
+      st_s[j] = 0.f;
+      st_q[j] = 0.f;
     }
-    uint32_t it = 0;
-    for (int t = cluster_id; t < total; t += nclusters, ++it) {
+    const int st_cc = gtid & 7, st_row0 = gtid >> 3;
+    const float* bias_h = s_bias + half * 32;
+    uint8_t* sbuf = sO + grp * 16384;
+    uint32_t it = grp;
+    for (int t = cluster_id + grp * nclusters; t < total; t += 2 * nclusters, it += 2) {
       const int tx = t % p.tiles_w;
       const int rr = t / p.tiles_w;
       const int ty = rr % p.tiles_h;
       const int n = rr / p.tiles_h;
-      const uint32_t acc = it & 1, pacc = (it >> 1) & 1;
-      const int h = ty * 8 + 4 * static_cast<int>(rank) + q;
-      const int w = tx * kRtTileW + lane - 1;
-      const bool valid = lane >= 1 && lane <= kRtTileW && h < p.H && w < p.W;
-      const long long pixoff = valid ? (static_cast<long long>(n) * p.H + h) * p.W + w : 0;
+      const uint32_t acc = it % NACC, pacc = (it / NACC) & 1;
+      const int h0 = ty * 8 + 4 * static_cast<int>(rank);
+      const int w0 = tx * kRtTileW;
+      const bool out_lane = lane >= 1 && lane <= kRtTileW;
       mbar_wait(&acc_full[acc], pacc);
       tc_fence_after();
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 192 + half * 32;
-#pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        uint32_t vl[16], vc[16], vr[16];
-        tmem_ld16(tbase + part * 16, vl);        // E_0: tap s = 0 multiplies X[w - 1]
-        tmem_ld16(tbase + 64 + part * 16, vc);   // E_1
-        tmem_ld16(tbase + 128 + part * 16, vr);  // E_2: tap s = 2 multiplies X[w + 1]
-        tmem_ld_wait();
-        uint32_t pk[8];
-#pragma unroll
-        for (int jj = 0; jj < 8; ++jj) {
-          float x[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int j = 2 * jj + e;
-            const int c = half * 32 + part * 16 + j;
-            // lane l holds E_s at image column w0 - 1 + l; the output at lane l needs E_0 of lane l - 1 and E_2 of lane l + 1
-            float v = __shfl_up_sync(0xffffffffu, __uint_as_float(vl[j]), 1) + __uint_as_float(vc[j]) +
-                      __shfl_down_sync(0xffffffffu, __uint_as_float(vr[j]), 1) + s_bias[c];
-            if (p.relu) v = fmaxf(v, 0.f);
-            if (affine) v = fmaf(v, s_sum[c], s_sq[c]);
-            x[e] = v;
-          }
-          pk[jj] = pack_bf16x2(x[0], x[1]);
-        }
-        if (valid) {
-          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.dst0) + pixoff * p.ldc0 + half * 32 +
-                                              part * 16);
-          o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
-        if (do_stats && valid) {
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const float lo = bf16lo_to_f32(pk[jj]), hi = bf16hi_to_f32(pk[jj]);
-            ssum[part * 16 + 2 * jj] += lo;
-            ssum[part * 16 + 2 * jj + 1] += hi;
-            ssq[part * 16 + 2 * jj] = fmaf(lo, lo, ssq[part * 16 + 2 * jj]);
-            ssq[part * 16 + 2 * jj + 1] = fmaf(hi, hi, ssq[part * 16 + 2 * jj + 1]);
-          }
-        }
-      }
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 128 + half * 32;
+      uint32_t g0[32], g1[32];
+      tmem_ld32(tbase, g0);       // G0[l] belongs to the output one pixel to the right (lane l + 1)
+      tmem_ld32(tbase + 64, g1);  // G1[l] belongs to this lane's output
+      tmem_ld_wait();
+      // the accumulator stage is in registers: hand it back to the MMA thread before the arithmetic
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(&acc_empty[acc], 0);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) g0[j] = __float_as_uint(__shfl_up_sync(0xffffffffu, __uint_as_float(g0[j]), 1));
+      uint32_t pk[16];
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        float x[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = 2 * jj + e;
+          float v = (__uint_as_float(g0[j]) + __uint_as_float(g1[j])) + bias_h[j];
+          if (p.relu) v = fmaxf(v, 0.f);
+          if (affine) v = fmaf(v, s_sum[half * 32 + j], s_sq[half * 32 + j]);
+          x[e] = v;
+        }
+        pk[jj] = pack_bf16x2(x[0], x[1]);
+      }
+      // stage the tile in shared memory in the SWIZZLE_128B pattern of the store map (row = pixel, 16-byte chunk
+      // index XOR row % 8: conflict-free), then ONE TMA store per CTA and tile writes full 128-byte lines and clips
+      // at the image border; scattered 16-byte stores at a 128-byte stride were measured to cost ~1000 clk per tile.
+      // The group's previous store (two tiles ago) has long finished reading this buffer: the wait below is free.
+      if (gtid == 0) tma_store_wait_read<0>();
+      named_bar_sync(2 + grp, 256);
+      if (out_lane) {
+        const int row = q * kRtTileW + lane - 1;
+        uint8_t* rp = sbuf + row * 128;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+          *reinterpret_cast<uint4*>(rp + (((half * 4 + jj) ^ (row & 7)) << 4)) =
+              make_uint4(pk[4 * jj], pk[4 * jj + 1], pk[4 * jj + 2], pk[4 * jj + 3]);
+      }
+      fence_proxy_async();
+      named_bar_sync(2 + grp, 256);
+      if (gtid == 0) {
+        tma_store_5d(&mapO, sbuf, 0, w0, h0, n, 0);
+        tma_store_commit();
+      }
+      if (do_stats) {
+        const bool interior = h0 + 4 <= p.H && w0 + kRtTileW <= p.W;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = st_row0 + 32 * i;
+          bool ok = row < 4 * kRtTileW;
+          if (ok && !interior) {
+            const int qr = row / kRtTileW, px = row - qr * kRtTileW;
+            ok = h0 + qr < p.H && w0 + px < p.W;
+          }
+          if (ok) {
+            const uint4 v = *reinterpret_cast<const uint4*>(sbuf + row * 128 + ((st_cc ^ (row & 7)) << 4));
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const float lo = bf16lo_to_f32(u[jj]), hi = bf16hi_to_f32(u[jj]);
+              st_s[2 * jj] += lo;
+              st_s[2 * jj + 1] += hi;
+              st_q[2 * jj] = fmaf(lo, lo, st_q[2 * jj]);
+              st_q[2 * jj + 1] = fmaf(hi, hi, st_q[2 * jj + 1]);
+            }
+          }
+        }
+      }
     }
+    if (gtid == 0) tma_store_wait<0>();
     if (do_stats) {
-      // one cross-lane reduction per CTA: column sums of the per-thread partials, then 4 warps per channel half meet
-      // in shared memory, then ONE fp64 atomic per channel and CTA
-      const float s = warp_colsum32(ssum, lane);
-      const float sq = warp_colsum32(ssq, lane);
-      atomicAdd(&s_sum[half * 32 + lane], s);
-      atomicAdd(&s_sq[half * 32 + lane], sq);
-      named_bar_sync(1, kC3EpiThreads);
-      for (int i = etid; i < 64; i += kC3EpiThreads) {
+      // lanes l, l + 8, l + 16, l + 24 hold the same chunk column: fold them, then the 16 warps meet in shared memory,
+      // then ONE fp64 atomic per channel and CTA
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        st_s[j] += __shfl_xor_sync(0xffffffffu, st_s[j], 8);
+        st_s[j] += __shfl_xor_sync(0xffffffffu, st_s[j], 16);
+        st_q[j] += __shfl_xor_sync(0xffffffffu, st_q[j], 8);
+        st_q[j] += __shfl_xor_sync(0xffffffffu, st_q[j], 16);
+      }
+      if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(&s_sum[lane * 8 + j], st_s[j]);
+          atomicAdd(&s_sq[lane * 8 + j], st_q[j]);
+        }
+      }
+      named_bar_sync(1, kRtEpiThreads);
+      for (int i = etid; i < 64; i += kRtEpiThreads) {
         if (i < p.n_store) {
           atomicAdd(&p.stat_sum[i], static_cast<double>(s_sum[i]));
           atomicAdd(&p.stat_sq[i], static_cast<double>(s_sq[i]));
@@ -1746,10 +1818,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
   if (warp == 1) tmem_dealloc_2cta(tmem_base, TMEM_COLS);
 }
 
-// a0/a1 box {64, 32, 6, 1, 1}; b = the packed weights viewed as [3][192][K], box {64, 96, 1}; p.tiles_w = ceil(W / 30),
-// p.tiles_h = ceil(H / 8), p.m_tiles = N * tiles_h * tiles_w; kc0 + kc1 <= 2; single destination, 64 columns.
-cudaError_t launch_conv3r(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const Conv3Params& p,
-                          int num_sms, cudaStream_t st) {
+// a0/a1 box {64, 32, 6, 1, 1}; b = the packed weights viewed as [3][192][K], box {64, 32, 1}; p.tiles_w = ceil(W / 30),
+// p.tiles_h = ceil(H / 8), p.m_tiles = N * tiles_h * tiles_w; kc0 + kc1 <= 2; o = the [N][H][W][64] destination, box
+// {64, 30, 4, 1, 1}.
+cudaError_t launch_conv3r(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                          const Conv3Params& p, int num_sms, cudaStream_t st) {
   if (p.kc0 + p.kc1 > kRtMaxKc || p.split_c != 0 || p.n_store > 64) return cudaErrorInvalidValue;
   static PerDeviceOnce attr_once;
   if (attr_once.first()) {
@@ -1758,7 +1831,7 @@ cudaError_t launch_conv3r(const CUtensorMap& a0, const CUtensorMap& a1, const CU
   }
   int clusters = p.m_tiles;
   if (clusters > num_sms / 2) clusters = num_sms / 2;
-  launch_k(igemm_conv3r_kernel, dim3(2 * clusters), dim3(kC3Threads), kRtSmem, st, a0, a1, b, p);
+  launch_k(igemm_conv3r_kernel, dim3(2 * clusters), dim3(kRtThreads), kRtSmem, st, a0, a1, b, o, p);
   return cudaGetLastError();
 }
 

@@ -119,8 +119,8 @@ struct Conv3Params {
 cudaError_t launch_conv3x2(int BN, int SUB, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                            const Conv3Params& p, int num_sms, cudaStream_t st);
 // row-tap variant for 64 output channels (three horizontal taps per MMA, N = 192), see igemm_conv3r_kernel
-cudaError_t launch_conv3r(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const Conv3Params& p,
-                          int num_sms, cudaStream_t st);
+cudaError_t launch_conv3r(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& o,
+                          const Conv3Params& p, int num_sms, cudaStream_t st);
 cudaError_t launch_conv3(int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                          const Conv3Params& p, int num_sms, cudaStream_t st);
 

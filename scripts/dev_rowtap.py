@@ -1,5 +1,5 @@
-"""row-tap kernel (igemm_conv3r_kernel) vs the tap-by-tap pair kernel: correctness on odd shapes + timing at the
-benchmark shapes.  usage: python scripts/dev_rowtap.py"""
+"""paired-tap kernel for 64-output-channel conv3x3 layers (igemm_conv3r_kernel) vs the tap-by-tap pair kernel:
+correctness on odd shapes + timing at the benchmark shapes.  usage: python scripts/dev_rowtap.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
