@@ -240,7 +240,7 @@ def run_b200(args):
     if args.continual:  # BASELINE config 3: + frozen previous-task network UNet(16) in eval mode, T = 2, lambda = 1
         old_model = clk.UNet(16).to(dev)
         old_model.eval()
-    ts = clk.TrainStep(model, opt, old_model=old_model, T=2.0, lam=1.0, use_graph=(world == 1 and not args.no_graph),
+    ts = clk.TrainStep(model, opt, old_model=old_model, T=2.0, lam=1.0, use_graph=not args.no_graph,
                        comm=comm)
 
     # synthetic VOC-shaped data: a few distinct batches per rank, resident in HBM for `value`,

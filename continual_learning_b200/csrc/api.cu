@@ -864,6 +864,16 @@ int clk_maxpool_bwd_add(const void* dpooled, const void* idx, const void* skip, 
   REQ_C8("maxpool_bwd_add", C);
   return cuda_status(maxpool_bwd_add(dpooled, idx, skip, din, N, H, W, C, S(st)), "maxpool_bwd_add");
 }
+int clk_maxpool_bwd_add_reduce(const void* dpooled, const void* idx, const void* skip, const void* y, void* din,
+                               double* s1, double* s2, int N, int H, int W, int C, clk_stream_t st) {
+  if (!dpooled || !idx || !din || !y || !s1 || !s2 || N <= 0) return fail(CLK_E_BADARG, "maxpool_bwd_add_reduce: bad args");
+  if (H % 2 || W % 2) return fail(CLK_E_UNSUPPORTED_SHAPE, "maxpool_bwd_add_reduce: H and W must be even");
+  REQ_C8("maxpool_bwd_add_reduce", C);
+  if (C > 2048 || 256 % (C / 8) != 0)
+    return fail(CLK_E_UNSUPPORTED_SHAPE, "maxpool_bwd_add_reduce: C / 8 must divide 256 (C=%d)", C);
+  return cuda_status(maxpool_bwd_add_reduce(dpooled, idx, skip, y, din, s1, s2, N, H, W, C, S(st)),
+                     "maxpool_bwd_add_reduce");
+}
 int clk_bn_bwd_reduce(const void* dz, const void* y, double* s1, double* s2, long long P, int C,
                       clk_stream_t st) {
   if (!dz || !y || !s1 || !s2 || P <= 0) return fail(CLK_E_BADARG, "bn_bwd_reduce: bad args");

@@ -509,6 +509,89 @@ cudaError_t maxpool_bwd_add(const void* dpooled, const void* idx, const void* sk
   return cudaGetLastError();
 }
 
+// The same, fused with the BatchNorm-backward reductions of the layer whose output was pooled (the gradient `din` it
+// writes IS that layer's dz): S1 += sum din, S2 += sum din * y per channel, on the bf16 values it stores, so the separate
+// bn_bwd_reduce pass over (dz, y) becomes one extra read of y here (2 instead of 4 bytes per element, one launch less).
+// 256 threads, 256 % CV == 0: a thread keeps its vector column cv for the whole grid-stride loop.
+__global__ void __launch_bounds__(256)
+    maxpool_bwd_add_reduce_kernel(const uint4* __restrict__ dpooled, const uint2* __restrict__ idx,
+                                  const uint4* __restrict__ skip, const uint4* __restrict__ y, uint4* __restrict__ din,
+                                  double* __restrict__ s1, double* __restrict__ s2, int N, int H, int W, int CV) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float red[];  // [rows][CV * 16]
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = static_cast<long long>(N) * Ho * Wo * CV;
+  float acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.f;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % CV);
+    long long r = i / CV;
+    const int wo = static_cast<int>(r % Wo);
+    r /= Wo;
+    const int ho = static_cast<int>(r % Ho);
+    const long long n = r / Ho;
+    float g[8];
+    unpack8(ldg_stream(dpooled + i), g);
+    const uint2 id = idx[i];
+    uint32_t bi[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      bi[e] = (id.x >> (8 * e)) & 0xFF;
+      bi[4 + e] = (id.y >> (8 * e)) & 0xFF;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const long long pix = (n * H + 2 * ho + (k >> 1)) * W + 2 * wo + (k & 1);
+      float f[8], yv[8];
+      if (skip != nullptr) {
+        unpack8(ldg_stream(skip + pix * CV + cv), f);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = 0.f;
+      }
+      unpack8(ldg_stream(y + pix * CV + cv), yv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (bi[e] == static_cast<uint32_t>(k)) f[e] += g[e];
+      const uint4 pk = pack8(f);
+      din[pix * CV + cv] = pk;
+      unpack8(pk, f);  // the reductions see exactly what a later pass over the stored tensor would
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        acc[e] += f[e];
+        acc[8 + e] = fmaf(f[e], yv[e], acc[8 + e]);
+      }
+    }
+  }
+  const int rows = blockDim.x / CV;
+  const int cv = threadIdx.x % CV;
+  const int rr = threadIdx.x / CV;
+  const int width = CV * 16;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) red[rr * width + (e / 8) * CV * 8 + cv * 8 + (e % 8)] = acc[e];
+  __syncthreads();
+  for (int i = threadIdx.x; i < width; i += blockDim.x) {
+    float s = 0.f;
+    for (int q = 0; q < rows; ++q) s += red[q * width + i];
+    const int which = i / (CV * 8), c = i % (CV * 8);
+    atomicAdd((which == 0 ? s1 : s2) + c, static_cast<double>(s));
+  }
+}
+cudaError_t maxpool_bwd_add_reduce(const void* dpooled, const void* idx, const void* skip, const void* y, void* din,
+                                   double* s1, double* s2, int N, int H, int W, int C, cudaStream_t st) {
+  const int CV = C / 8;
+  if (CV < 1 || 256 % CV != 0) return cudaErrorInvalidValue;
+  const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * CV;
+  const size_t smem = static_cast<size_t>(256 / CV) * CV * 16 * sizeof(float);
+  launch_k(maxpool_bwd_add_reduce_kernel, dim3(grid_for(total, 256 * 2, 8)), dim3(256), smem, st,
+           static_cast<const uint4*>(dpooled), static_cast<const uint2*>(idx), static_cast<const uint4*>(skip),
+           static_cast<const uint4*>(y), static_cast<uint4*>(din), s1, s2, N, H, W, CV);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // per-channel reductions over NHWC bf16.  Block = 256 threads = (256/CV) pixel rows x CV vector
 // columns (CV = C/8 <= 256); each thread keeps 8 (or 16) fp32 partials, rows are folded through

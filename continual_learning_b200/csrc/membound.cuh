@@ -32,6 +32,8 @@ cudaError_t bn_apply(const void* y, void* z, const float* scale, const float* sh
                      cudaStream_t st);
 cudaError_t bn_apply_pool(const void* y, void* z, void* pooled, void* idx, const float* scale,
                           const float* shift, int N, int H, int W, int C, cudaStream_t st);
+cudaError_t maxpool_bwd_add_reduce(const void* dpooled, const void* idx, const void* skip, const void* y, void* din,
+                                   double* s1, double* s2, int N, int H, int W, int C, cudaStream_t st);
 cudaError_t maxpool_bwd_add(const void* dpooled, const void* idx, const void* skip, void* din, int N,
                             int H, int W, int C, cudaStream_t st);
 cudaError_t bn_stats(const void* y, double* sum, double* sq, long long P, int C, cudaStream_t st);

@@ -376,10 +376,12 @@ class UNetEngine:
             after_group(g)
 
     # ------------------------------------------------------------------ backward
-    def _unit_bwd(self, u, dz, need_dx=True):
+    def _unit_bwd(self, u, dz, need_dx=True, reduced=False):
+        """reduced=True: the producer of dz already accumulated s1 = sum dz and s2 = sum dz * y (maxpool_bwd_add_reduce)."""
         n, h, w = dz.shape[0], dz.shape[1], dz.shape[2]
         bn = u.bn
-        ops.bn_bwd_reduce(dz, u.y, u.s1, u.s2)
+        if not reduced:
+            ops.bn_bwd_reduce(dz, u.y, u.s1, u.s2)
         if not self.fuse_bn:
             ka, kb, kc = u.vec[4], u.vec[5], u.vec[6]
             ops.bn_bwd_finalize(u.s1, u.s2, bn.weight.detach(), u.vec[0], u.vec[1], self.gview[bn.weight],
@@ -506,8 +508,12 @@ class UNetEngine:
         yield 0
         # encoder, deepest first: enc4 (U[7]) .. enc1 (U[1])
         for lvl, k in ((3, 7), (2, 5), (1, 3), (0, 1)):
-            dz = ops.maxpool_bwd_add(dpool, U[k].idx, skip_grads[lvl])
-            dz, _ = self._unit_bwd(U[k], dz)
+            fuse = (U[k].cout // 8) in (8, 16, 32, 64, 128, 256) and not self.fuse_bn
+            if fuse:  # max-pool backward + skip sum + the BatchNorm-backward reductions of U[k] in one pass
+                dz = ops.maxpool_bwd_add_reduce(dpool, U[k].idx, skip_grads[lvl], U[k].y, U[k].s1, U[k].s2)
+            else:
+                dz = ops.maxpool_bwd_add(dpool, U[k].idx, skip_grads[lvl])
+            dz, _ = self._unit_bwd(U[k], dz, reduced=fuse)
             dpool, _ = self._unit_bwd(U[k - 1], dz, need_dx=(k > 1))
             if k == 7:
                 self._flush_grads(1)  # enc4: 11 % of the parameters, final long before the backward pass ends

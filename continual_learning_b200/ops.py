@@ -288,6 +288,15 @@ def maxpool_bwd_add(dpooled, idx, skip, out=None):
     return din
 
 
+def maxpool_bwd_add_reduce(dpooled, idx, skip, y, s1, s2, out=None):
+    """maxpool_bwd_add + the BatchNorm-backward reductions of the pooled layer in one pass (s1 += sum din,
+    s2 += sum din * y)."""
+    n, ho, wo, c = dpooled.shape
+    din = torch.empty((n, 2 * ho, 2 * wo, c), device=dpooled.device, dtype=bf16) if out is None else out
+    _lib.call("clk_maxpool_bwd_add_reduce", dpooled, idx, skip, y, din, s1, s2, n, 2 * ho, 2 * wo, c)
+    return din
+
+
 def bn_bwd_reduce(dz, y, s1, s2):
     c = y.shape[-1]
     _lib.call("clk_bn_bwd_reduce", dz, y, s1, s2, y.numel() // c, c)

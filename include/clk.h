@@ -173,6 +173,11 @@ int clk_bn_relu_bwd_apply_fused(const void* dz, const void* y, void* dpre, const
  * skip-connection gradient sum. */
 int clk_maxpool_bwd_add(const void* dpooled, const void* idx, const void* skip, void* din, int N, int H,
                         int W, int C, clk_stream_t st);
+/* the same, fused with the BatchNorm-backward reductions of the pooled layer (models/unet.py:12,15): din is that
+ * layer's dz, so s1 f64[C] += sum din and s2 f64[C] += sum din * y (y = the layer's relu(conv) output, bf16 [N][H][W][C])
+ * are accumulated on the values stored, and clk_bn_bwd_reduce need not run.  C / 8 must divide 256. */
+int clk_maxpool_bwd_add_reduce(const void* dpooled, const void* idx, const void* skip, const void* y, void* din,
+                               double* s1, double* s2, int N, int H, int W, int C, clk_stream_t st);
 int clk_bn_bwd_reduce(const void* dz, const void* y, double* s1, double* s2, long long P, int C,
                       clk_stream_t st);
 int clk_bn_bwd_finalize(const double* s1, const double* s2, const float* gamma, const float* mean,

@@ -289,6 +289,16 @@ def test_batchnorm_train_forward_backward_pool(ops, n, h, w, c):
     dp, skip = bfr(rnd(g, n, c, h // 2, w // 2)), bfr(rnd(g, n, c, h, w))
     din = ops.maxpool_bwd_add(to_nhwc_dev(dp), idx, to_nhwc_dev(skip))
     assert rel(from_nhwc(din), F.max_unpool2d(dp, ir, 2, 2) + skip) <= BF16_TOL
+    # ... and with the BatchNorm-backward reductions of the pooled layer (din is its dz): same tensor, and the sums of
+    # a separate clk_bn_bwd_reduce pass over (din, y)
+    r1, r2 = (torch.zeros(c, device=dev, dtype=torch.float64) for _ in range(2))
+    din2 = ops.maxpool_bwd_add_reduce(to_nhwc_dev(dp), idx, to_nhwc_dev(skip), yd, r1, r2)
+    assert torch.equal(din2, din)
+    w1, w2 = (torch.zeros(c, device=dev, dtype=torch.float64) for _ in range(2))
+    ops.bn_bwd_reduce(din, yd, w1, w2)
+    assert rel(r1, w1) <= 1e-5 and rel(r2, w2) <= 1e-5   # fp32 partial sums in a different order, fp64 totals
+    dd, yy = din.double().reshape(-1, c), yd.double().reshape(-1, c)
+    assert rel(r1, dd.sum(0)) <= 1e-5 and rel(r2, (dd * yy).sum(0)) <= 1e-5
 
 
 def test_batchnorm_eval_mode_uses_running_stats(ops):
