@@ -53,9 +53,6 @@ SIGNATURES = {
     "clk_bn_finalize": [p, p, p, p, p, p, p, p, p, p, i, d, f, f, i, p],
     "clk_bn_apply": [p, p, p, p, ll, i, p],
     "clk_bn_apply_pool": [p, p, p, p, p, p, i, i, i, i, p],
-    "clk_bn_apply_fused": [p, p, p, p, p, p, p, p, p, p, ll, i, d, f, f, i, p],
-    "clk_bn_apply_pool_fused": [p, p, p, p, p, p, p, p, p, p, p, p, i, i, i, i, d, f, f, i, p],
-    "clk_bn_relu_bwd_apply_fused": [p, p, p, p, p, p, p, p, p, p, p, ll, i, d, i, p],
     "clk_maxpool_bwd_add": [p, p, p, p, i, i, i, i, p],
     "clk_maxpool_bwd_add_reduce": [p, p, p, p, p, p, p, i, i, i, i, p],
     "clk_bn_bwd_reduce": [p, p, p, p, ll, i, p],

@@ -822,41 +822,6 @@ int clk_bn_apply_pool(const void* y, void* z, void* pooled, void* idx, const flo
   REQ_C8("bn_apply_pool", C);
   return cuda_status(bn_apply_pool(y, z, pooled, idx, scale, shift, N, H, W, C, S(st)), "bn_apply_pool");
 }
-int clk_bn_apply_fused(const void* y, void* z, const double* sum, const double* sq, const float* gamma,
-                       const float* beta, float* running_mean, float* running_var, float* mean_out, float* invstd_out,
-                       long long P, int C, double count, float eps, float momentum, int training, clk_stream_t st) {
-  if (!y || !z || !gamma || !beta || !mean_out || !invstd_out || P <= 0) return fail(CLK_E_BADARG, "bn_apply_fused: bad args");
-  if (training && (!sum || !sq || count <= 0)) return fail(CLK_E_BADARG, "bn_apply_fused: training needs sums");
-  if (!training && (!running_mean || !running_var)) return fail(CLK_E_BADARG, "bn_apply_fused: eval needs running stats");
-  REQ_C8("bn_apply_fused", C);
-  return cuda_status(bn_apply_fused(y, z, sum, sq, gamma, beta, running_mean, running_var, mean_out, invstd_out, P, C,
-                                    count, eps, momentum, training, S(st)),
-                     "bn_apply_fused");
-}
-int clk_bn_apply_pool_fused(const void* y, void* z, void* pooled, void* idx, const double* sum, const double* sq,
-                            const float* gamma, const float* beta, float* running_mean, float* running_var,
-                            float* mean_out, float* invstd_out, int N, int H, int W, int C, double count, float eps,
-                            float momentum, int training, clk_stream_t st) {
-  if (!y || !z || !pooled || !idx || !gamma || !beta || !mean_out || !invstd_out || N <= 0)
-    return fail(CLK_E_BADARG, "bn_apply_pool_fused: bad args");
-  if (training && (!sum || !sq || count <= 0)) return fail(CLK_E_BADARG, "bn_apply_pool_fused: training needs sums");
-  if (!training && (!running_mean || !running_var)) return fail(CLK_E_BADARG, "bn_apply_pool_fused: eval needs running stats");
-  if (H % 2 || W % 2) return fail(CLK_E_UNSUPPORTED_SHAPE, "bn_apply_pool_fused: H and W must be even");
-  REQ_C8("bn_apply_pool_fused", C);
-  return cuda_status(bn_apply_pool_fused(y, z, pooled, idx, sum, sq, gamma, beta, running_mean, running_var, mean_out,
-                                         invstd_out, N, H, W, C, count, eps, momentum, training, S(st)),
-                     "bn_apply_pool_fused");
-}
-int clk_bn_relu_bwd_apply_fused(const void* dz, const void* y, void* dpre, const double* s1, const double* s2,
-                                const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
-                                double* dbias, long long P, int C, double count, int training, clk_stream_t st) {
-  if (!dz || !y || !dpre || !s1 || !s2 || !gamma || !mean || !invstd || !dgamma || !dbeta || !dbias || P <= 0 || count <= 0)
-    return fail(CLK_E_BADARG, "bn_relu_bwd_apply_fused: bad args");
-  REQ_C8("bn_relu_bwd_apply_fused", C);
-  return cuda_status(bn_relu_bwd_apply_fused(dz, y, dpre, s1, s2, gamma, mean, invstd, dgamma, dbeta, dbias, P, C, count,
-                                             training, S(st)),
-                     "bn_relu_bwd_apply_fused");
-}
 int clk_maxpool_bwd_add(const void* dpooled, const void* idx, const void* skip, void* din, int N, int H, int W,
                         int C, clk_stream_t st) {
   if (!dpooled || !idx || !din || N <= 0) return fail(CLK_E_BADARG, "maxpool_bwd_add: bad args");

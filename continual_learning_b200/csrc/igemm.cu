@@ -1314,7 +1314,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
         for (int ch = 0; ch < kc; ++ch) {
           const uint32_t sa = ia % AS, pa = (ia / AS) & 1;
           mbar_wait(&a_full[sa], pa);
-          const uint32_t abase = smem_u32(sA + sa * kX2ABytes);
+          // all operand tiles lie below 256 KB, so moving a descriptor inside its tile is ONE add on the 14-bit
+          // start-address field (>> 4): the single issuing thread stays well ahead of the tensor pipe
+          const uint64_t adesc0 = umma_smem_desc(smem_u32(sA + sa * kX2ABytes), 16, PITCH * 128);
 #pragma unroll 1
           for (int tr = 0; tr < 3; ++tr) {
 #pragma unroll 1
@@ -1322,14 +1324,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC3Threads, 1)
               const uint32_t sb = ib % NB, pb = (ib / NB) & 1;
               mbar_wait(&b_full[sb], pb);
               tc_fence_after();
-              const uint32_t a = abase + (tr * PITCH + tsx) * 128;
-              const uint32_t b = smem_u32(sB + sb * B_BYTES);
+              const uint64_t adesc = adesc0 + static_cast<uint64_t>(((tr * PITCH + tsx) * 128) >> 4);
+              const uint64_t bdesc = umma_smem_desc(smem_u32(sB + sb * B_BYTES), 16, 1024);
 #pragma unroll
               for (int j = 0; j < SUB; ++j) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  umma_bf16_2cta(d0 + j * BN, umma_smem_desc(a + j * 1024 + k * 32, 16, PITCH * 128),
-                                 umma_smem_desc(b + k * 32, 16, 1024), idesc, (ch | tr | tsx | k) != 0 ? 1u : 0u);
+                  umma_bf16_2cta(d0 + j * BN, adesc + static_cast<uint64_t>((j * 1024 + k * 32) >> 4),
+                                 bdesc + static_cast<uint64_t>((k * 32) >> 4), idesc, (ch | tr | tsx | k) != 0 ? 1u : 0u);
                 }
               }
               umma_commit_2cta(&b_empty[sb]);

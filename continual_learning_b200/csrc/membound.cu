@@ -1178,248 +1178,6 @@ cudaError_t adam_multi_tensor(const AdamTensor* tensors, const void* blocks, int
 }
 
 // ------------------------------------------------------------------------------------------
-// fused-finalize variants: the per-channel coefficient computation of bn_finalize / bn_bwd_finalize is done
-// in the prologue of the streaming kernel itself (every thread needs the coefficients of ITS 8 channels only),
-// block 0 writes the per-channel outputs.  Removes 36 tiny dependent launches per training step.
-struct BnCoef {
-  float a[8], c[8];
-};
-__device__ __forceinline__ void bn_fwd_coef(const double* __restrict__ sum, const double* __restrict__ sq,
-                                            const float* __restrict__ gamma, const float* __restrict__ beta,
-                                            float* __restrict__ rmean, float* __restrict__ rvar,
-                                            float* __restrict__ mean_out, float* __restrict__ invstd_out, int c0,
-                                            double count, float eps, float momentum, int training, bool writer,
-                                            BnCoef& k) {
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = c0 + e;
-    float mean, invstd;
-    if (training) {
-      const double m = sum[c] / count;
-      double var = sq[c] / count - m * m;
-      if (var < 0.0) var = 0.0;
-      mean = static_cast<float>(m);
-      invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
-      if (writer && rmean != nullptr) {
-        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-        rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
-        rvar[c] = (1.f - momentum) * rvar[c] + momentum * static_cast<float>(unbiased);
-      }
-    } else {
-      mean = rmean[c];
-      invstd = 1.f / sqrtf(rvar[c] + eps);
-    }
-    if (writer) {
-      mean_out[c] = mean;
-      invstd_out[c] = invstd;
-    }
-    k.a[e] = gamma[c] * invstd;
-    k.c[e] = beta[c] - mean * k.a[e];
-  }
-}
-
-__global__ void __launch_bounds__(256)
-    bn_apply_fused_kernel(const uint4* __restrict__ y, uint4* __restrict__ z, const double* __restrict__ sum,
-                          const double* __restrict__ sq, const float* __restrict__ gamma,
-                          const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
-                          float* __restrict__ mean_out, float* __restrict__ invstd_out, long long nvec, int CV,
-                          double count, float eps, float momentum, int training) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int cv = CV - 1 - (threadIdx.x % CV);
-  BnCoef k;
-  // in training mode the running statistics are read-modify-written by block 0 only; other blocks never read them
-  bn_fwd_coef(sum, sq, gamma, beta, rmean, rvar, mean_out, invstd_out, cv * 8, count, eps, momentum, training,
-              blockIdx.x == 0 && threadIdx.x < CV, k);
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long j = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; j < nvec; j += 2 * stride) {
-    const bool two = j + stride < nvec;
-    const long long i = nvec - 1 - j - (two ? stride : 0);
-    const uint4 v0 = ldg_stream(y + i);
-    const uint4 v1 = two ? ldg_stream(y + i + stride) : make_uint4(0, 0, 0, 0);
-    float f[8];
-    unpack8(v0, f);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], k.a[e], k.c[e]);
-    z[i] = pack8(f);
-    if (two) {
-      unpack8(v1, f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], k.a[e], k.c[e]);
-      z[i + stride] = pack8(f);
-    }
-  }
-}
-cudaError_t bn_apply_fused(const void* y, void* z, const double* sum, const double* sq, const float* gamma,
-                           const float* beta, float* rmean, float* rvar, float* mean_out, float* invstd_out,
-                           long long P, int C, double count, float eps, float momentum, int training,
-                           cudaStream_t st) {
-  const int CV = C / 8;
-  if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
-  const long long nvec = P * CV;
-  const int threads = (256 / CV) * CV;
-  launch_k(bn_apply_fused_kernel, dim3(grid_for(nvec, threads * 4, 8)), dim3(threads), 0, st, 
-      static_cast<const uint4*>(y), static_cast<uint4*>(z), sum, sq, gamma, beta, rmean, rvar, mean_out, invstd_out,
-      nvec, CV, count, eps, momentum, training);
-  return cudaGetLastError();
-}
-
-__global__ void __launch_bounds__(256)
-    bn_apply_pool_fused_kernel(const uint4* __restrict__ y, uint4* __restrict__ z, uint4* __restrict__ pooled,
-                               uint2* __restrict__ idx, const double* __restrict__ sum, const double* __restrict__ sq,
-                               const float* __restrict__ gamma, const float* __restrict__ beta,
-                               float* __restrict__ rmean, float* __restrict__ rvar, float* __restrict__ mean_out,
-                               float* __restrict__ invstd_out, int N, int H, int W, int CV, double count, float eps,
-                               float momentum, int training) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int Ho = H / 2, Wo = W / 2;
-  const long long total = static_cast<long long>(N) * Ho * Wo * CV;
-  const int cv = threadIdx.x % CV;  // blockDim is a multiple of CV
-  BnCoef k;
-  bn_fwd_coef(sum, sq, gamma, beta, rmean, rvar, mean_out, invstd_out, cv * 8, count, eps, momentum, training,
-              blockIdx.x == 0 && threadIdx.x < CV, k);
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    long long r = i / CV;
-    const int wo = static_cast<int>(r % Wo);
-    r /= Wo;
-    const int ho = static_cast<int>(r % Ho);
-    const long long n = r / Ho;
-    float best[8];
-    uint32_t bidx[8];
-    uint4 raw[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      raw[q] = ldg_stream(y + ((n * H + 2 * ho + (q >> 1)) * W + 2 * wo + (q & 1)) * CV + cv);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const long long pix = (n * H + 2 * ho + (q >> 1)) * W + 2 * wo + (q & 1);
-      float f[8];
-      unpack8(raw[q], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = fmaf(f[e], k.a[e], k.c[e]);
-      const uint4 zz = pack8(f);
-      z[pix * CV + cv] = zz;
-      unpack8(zz, f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (q == 0 || f[e] > best[e] || f[e] != f[e]) {
-          best[e] = f[e];
-          bidx[e] = q;
-        }
-      }
-    }
-    pooled[i] = pack8(best);
-    uint2 id;
-    id.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
-    id.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
-    idx[i] = id;
-  }
-}
-cudaError_t bn_apply_pool_fused(const void* y, void* z, void* pooled, void* idx, const double* sum,
-                                const double* sq, const float* gamma, const float* beta, float* rmean, float* rvar,
-                                float* mean_out, float* invstd_out, int N, int H, int W, int C, double count,
-                                float eps, float momentum, int training, cudaStream_t st) {
-  const int CV = C / 8;
-  if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
-  const long long total = static_cast<long long>(N) * (H / 2) * (W / 2) * CV;
-  const int threads = (256 / CV) * CV;
-  launch_k(bn_apply_pool_fused_kernel, dim3(grid_for(total, threads * 2, 8)), dim3(threads), 0, st, 
-      static_cast<const uint4*>(y), static_cast<uint4*>(z), static_cast<uint4*>(pooled), static_cast<uint2*>(idx),
-      sum, sq, gamma, beta, rmean, rvar, mean_out, invstd_out, N, H, W, CV, count, eps, momentum, training);
-  return cudaGetLastError();
-}
-
-// BatchNorm + ReLU backward with the finalize folded in: coefficients from (s1, s2) in the prologue,
-// block 0 writes dgamma / dbeta.
-__global__ void __launch_bounds__(256, 4)
-    bn_relu_bwd_apply_fused_kernel(const uint4* __restrict__ dz, const uint4* __restrict__ y, uint4* __restrict__ dpre,
-                                   const double* __restrict__ s1, const double* __restrict__ s2,
-                                   const float* __restrict__ gamma, const float* __restrict__ mean,
-                                   const float* __restrict__ invstd, float* __restrict__ dgamma,
-                                   float* __restrict__ dbeta, double* __restrict__ dbias, long long P, int CV,
-                                   double count, int training) {
-  pdl_launch_dependents();
-  pdl_wait();
-  extern __shared__ float red[];
-  const int rows = blockDim.x / CV;
-  const int cv = threadIdx.x % CV;
-  const int r = threadIdx.x / CV;
-  float ka[8], kb[8], kc[8], acc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int c = cv * 8 + e;
-    const double mu = mean[c], is = invstd[c], g = gamma[c];
-    const double a = s1[c], b = s2[c];
-    const double dg = is * (b - mu * a);
-    if (blockIdx.x == 0 && r == 0) {
-      dgamma[c] = static_cast<float>(dg);
-      dbeta[c] = static_cast<float>(a);
-    }
-    ka[e] = static_cast<float>(g * is);
-    kb[e] = training ? static_cast<float>(-g * is * is * dg / count) : 0.f;
-    kc[e] = training ? static_cast<float>(-g * is * a / count + g * is * is * mu * dg / count) : 0.f;
-    acc[e] = 0.f;
-  }
-  const long long stride = static_cast<long long>(gridDim.x) * rows;
-  for (long long p = blockIdx.x * static_cast<long long>(rows) + r; r < rows && p < P; p += 2 * stride) {
-    const bool two = p + stride < P;
-    const uint4 g0 = ldg_stream(dz + p * CV + cv), f0 = ldg_stream(y + p * CV + cv);
-    uint4 g1 = make_uint4(0, 0, 0, 0), f1 = g1;
-    if (two) {
-      g1 = ldg_stream(dz + (p + stride) * CV + cv);
-      f1 = ldg_stream(y + (p + stride) * CV + cv);
-    }
-    float g[8], f[8], o[8];
-    unpack8(g0, g);
-    unpack8(f0, f);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float d = fmaf(ka[e], g[e], fmaf(kb[e], f[e], kc[e]));
-      o[e] = f[e] > 0.f ? d : 0.f;
-      acc[e] += o[e];
-    }
-    dpre[p * CV + cv] = pack8(o);
-    if (two) {
-      unpack8(g1, g);
-      unpack8(f1, f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = fmaf(ka[e], g[e], fmaf(kb[e], f[e], kc[e]));
-        o[e] = f[e] > 0.f ? d : 0.f;
-        acc[e] += o[e];
-      }
-      dpre[(p + stride) * CV + cv] = pack8(o);
-    }
-  }
-  const int width = CV * 8;
-  if (r < rows) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) red[r * width + cv * 8 + e] = acc[e];
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < width; i += blockDim.x) {
-    float s = 0.f;
-    for (int rr = 0; rr < rows; ++rr) s += red[rr * width + i];
-    atomicAdd(dbias + i, static_cast<double>(s));
-  }
-}
-cudaError_t bn_relu_bwd_apply_fused(const void* dz, const void* y, void* dpre, const double* s1, const double* s2,
-                                    const float* gamma, const float* mean, const float* invstd, float* dgamma,
-                                    float* dbeta, double* dbias, long long P, int C, double count, int training,
-                                    cudaStream_t st) {
-  const int CV = C / 8;
-  if (CV > 256 || CV < 1) return cudaErrorInvalidValue;
-  const int rows = 256 / CV;
-  const size_t smem = static_cast<size_t>(rows) * CV * 8 * sizeof(float);
-  launch_k(bn_relu_bwd_apply_fused_kernel, dim3(grid_for(P, rows * 8, 4)), dim3(256), smem, st, 
-      static_cast<const uint4*>(dz), static_cast<const uint4*>(y), static_cast<uint4*>(dpre), s1, s2, gamma, mean,
-      invstd, dgamma, dbeta, dbias, P, CV, count, training);
-  return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------
 // table-driven batched variants: ONE launch packs / unpacks / converts every layer of the model
 // (per-layer launches of these tiny kernels cost more in launch latency than in bandwidth).
 // A job table is a device array of int64[16] rows; one thread block = one 32x32(xT) tile of one job.

@@ -58,18 +58,6 @@ cudaError_t argmax_confusion(const float* logits, const long long* labels, long 
 cudaError_t adam_multi_tensor(const AdamTensor* tensors, const void* blocks, int nblocks, int chunk,
                               float lr, float b1, float b2, float eps, float bc1, float bc2_sqrt,
                               float gscale, const float* hyper, cudaStream_t st);
-cudaError_t bn_apply_fused(const void* y, void* z, const double* sum, const double* sq, const float* gamma,
-                           const float* beta, float* rmean, float* rvar, float* mean_out, float* invstd_out,
-                           long long P, int C, double count, float eps, float momentum, int training,
-                           cudaStream_t st);
-cudaError_t bn_apply_pool_fused(const void* y, void* z, void* pooled, void* idx, const double* sum,
-                                const double* sq, const float* gamma, const float* beta, float* rmean, float* rvar,
-                                float* mean_out, float* invstd_out, int N, int H, int W, int C, double count,
-                                float eps, float momentum, int training, cudaStream_t st);
-cudaError_t bn_relu_bwd_apply_fused(const void* dz, const void* y, void* dpre, const double* s1, const double* s2,
-                                    const float* gamma, const float* mean, const float* invstd, float* dgamma,
-                                    float* dbeta, double* dbias, long long P, int C, double count, int training,
-                                    cudaStream_t st);
 cudaError_t pack_w_multi(const void* jobs, int njobs, int total_tiles, int max_T, cudaStream_t st);
 cudaError_t unpack_wgrad_multi(const void* jobs, int njobs, int total_tiles, int max_T, cudaStream_t st);
 cudaError_t reduce_partials_multi(const void* jobs, int njobs, int total_blocks, cudaStream_t st);

@@ -62,7 +62,6 @@ class UNetEngine:
         # BatchNorm statistics still use atomics) , ~0.15 ms/step slower
         self.deterministic = False
         self._forked = False
-        self.fuse_bn = False     # finalize folded into the apply kernels: measured 0.17 ms/step SLOWER (fp64 prologue per block)
         self.side_pack = True    # late-layer weight packing on the side stream
         self.training_fwd = True
         self.save_for_backward = True
@@ -278,20 +277,14 @@ class UNetEngine:
         else:
             u.y = ops.conv3x3_fprop(x0, x1, u.wf, bias, relu=True, stats=stats)
         bn = u.bn
-        if not self.fuse_bn:
-            mean, invstd, scale, shift = u.vec[0], u.vec[1], u.vec[2], u.vec[3]
-            ops.bn_finalize(u.s_sum, u.s_sq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, mean,
-                            invstd, scale, shift, n * h * w, eps=bn.eps,
-                            momentum=0.1 if bn.momentum is None else bn.momentum, training=training)
-            if pool:
-                u.z, u.pooled, u.idx = ops.bn_apply_pool(u.y, scale, shift)
-            else:
-                u.z, u.pooled, u.idx = ops.bn_apply(u.y, scale, shift), None, None
-            return u.z
-        u.z, u.pooled, u.idx = ops.bn_apply_fused(
-            u.y, u.s_sum, u.s_sq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, u.vec[0],
-            u.vec[1], n * h * w, eps=bn.eps, momentum=0.1 if bn.momentum is None else bn.momentum, training=training,
-            pool=pool)
+        mean, invstd, scale, shift = u.vec[0], u.vec[1], u.vec[2], u.vec[3]
+        ops.bn_finalize(u.s_sum, u.s_sq, bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, mean,
+                        invstd, scale, shift, n * h * w, eps=bn.eps,
+                        momentum=0.1 if bn.momentum is None else bn.momentum, training=training)
+        if pool:
+            u.z, u.pooled, u.idx = ops.bn_apply_pool(u.y, scale, shift)
+        else:
+            u.z, u.pooled, u.idx = ops.bn_apply(u.y, scale, shift), None, None
         return u.z
 
     def forward(self, x, training=True, save_for_backward=True, head=True):
@@ -382,13 +375,10 @@ class UNetEngine:
         bn = u.bn
         if not reduced:
             ops.bn_bwd_reduce(dz, u.y, u.s1, u.s2)
-        if not self.fuse_bn:
-            ka, kb, kc = u.vec[4], u.vec[5], u.vec[6]
-            ops.bn_bwd_finalize(u.s1, u.s2, bn.weight.detach(), u.vec[0], u.vec[1], self.gview[bn.weight],
-                                self.gview[bn.bias], ka, kb, kc, n * h * w, training=self.training_fwd)
-            dpre = ops.bn_relu_bwd_apply(dz, u.y, ka, kb, kc, u.dbias)
-        else:
-            dpre = self._bn_bwd_fused(u, dz, n * h * w)
+        ka, kb, kc = u.vec[4], u.vec[5], u.vec[6]
+        ops.bn_bwd_finalize(u.s1, u.s2, bn.weight.detach(), u.vec[0], u.vec[1], self.gview[bn.weight],
+                            self.gview[bn.bias], ka, kb, kc, n * h * w, training=self.training_fwd)
+        dpre = ops.bn_relu_bwd_apply(dz, u.y, ka, kb, kc, u.dbias)
         # the weight gradient only feeds the optimiser: run it on the side stream so that it overlaps the dgrad of
         # this layer and the (HBM-bound) BatchNorm backward of the next one
         with self._fork(dpre):
@@ -402,12 +392,6 @@ class UNetEngine:
         if u.stem or not need_dx:
             return None, None
         return ops.conv3x3_dgrad(dpre, u.wd, u.c0, u.c1)
-
-    def _bn_bwd_fused(self, u, dz, count):
-        bn = u.bn
-        return ops.bn_relu_bwd_apply_fused(dz, u.y, u.s1, u.s2, bn.weight.detach(), u.vec[0], u.vec[1],
-                                           self.gview[bn.weight], self.gview[bn.bias], u.dbias, count,
-                                           training=self.training_fwd)
 
     def _convT_bwd(self, j, dy):
         mod, cm, co = self.convT[j]
@@ -508,7 +492,7 @@ class UNetEngine:
         yield 0
         # encoder, deepest first: enc4 (U[7]) .. enc1 (U[1])
         for lvl, k in ((3, 7), (2, 5), (1, 3), (0, 1)):
-            fuse = (U[k].cout // 8) in (8, 16, 32, 64, 128, 256) and not self.fuse_bn
+            fuse = (U[k].cout // 8) in (8, 16, 32, 64, 128, 256)
             if fuse:  # max-pool backward + skip sum + the BatchNorm-backward reductions of U[k] in one pass
                 dz = ops.maxpool_bwd_add_reduce(dpool, U[k].idx, skip_grads[lvl], U[k].y, U[k].s1, U[k].s2)
             else:

@@ -256,31 +256,6 @@ def bn_apply_pool(y, scale, shift, z=None, pooled=None, idx=None):
     return z, pooled, idx
 
 
-def bn_apply_fused(y, s_sum, s_sq, gamma, beta, rmean, rvar, mean, invstd, count, eps=1e-5, momentum=0.1, training=True,
-                   pool=False):
-    """finalize + apply (+ 2x2 max-pool) in one launch; returns (z, pooled, idx)."""
-    n, h, w, c = y.shape
-    z = torch.empty_like(y)
-    if not pool:
-        _lib.call("clk_bn_apply_fused", y, z, s_sum, s_sq, gamma, beta, rmean, rvar, mean, invstd, n * h * w, c,
-                  float(count), float(eps), float(momentum), 1 if training else 0)
-        return z, None, None
-    pooled = torch.empty((n, h // 2, w // 2, c), device=y.device, dtype=bf16)
-    idx = torch.empty((n, h // 2, w // 2, c), device=y.device, dtype=torch.uint8)
-    _lib.call("clk_bn_apply_pool_fused", y, z, pooled, idx, s_sum, s_sq, gamma, beta, rmean, rvar, mean, invstd, n, h, w,
-              c, float(count), float(eps), float(momentum), 1 if training else 0)
-    return z, pooled, idx
-
-
-def bn_relu_bwd_apply_fused(dz, y, s1, s2, gamma, mean, invstd, dgamma, dbeta, dbias, count, training=True):
-    """bn_bwd_finalize + bn_relu_bwd_apply in one launch."""
-    c = y.shape[-1]
-    dpre = torch.empty_like(y)
-    _lib.call("clk_bn_relu_bwd_apply_fused", dz, y, dpre, s1, s2, gamma, mean, invstd, dgamma, dbeta, dbias,
-              y.numel() // c, c, float(count), 1 if training else 0)
-    return dpre
-
-
 def maxpool_bwd_add(dpooled, idx, skip, out=None):
     n, ho, wo, c = dpooled.shape
     din = torch.empty((n, 2 * ho, 2 * wo, c), device=dpooled.device, dtype=bf16) if out is None else out

@@ -37,7 +37,14 @@ int clk_version(void);
 const char* clk_last_error(void);
 /* CLK_OK iff device `dev` is compute capability 10.x; caches the SM count for grid sizing. */
 int clk_query_device(int dev);
-/* tuning knobs ("fprop_bn": force the N tile, 0 = auto; "wgrad_ksplit": force split-K, 0 = auto). */
+/* Developer knobs that select between kernel variants of the same operator (every variant computes the same
+ * function and is covered by tests/test_gpu_kernels.py): "conv3_v2" (0 generic per-tap kernel, 2 one-CTA halo kernel,
+ * 4 CTA-pair halo kernel = default), "conv3_pair", "conv3_rowtap" (1 = paired-tap kernel for 64-output-channel layers,
+ * default), "fprop_bn" (force the N tile, 0 = auto), "wgrad_v2", "wgrad_bn", "wgrad_ksplit", "wgrad_ctas",
+ * "conv3_min_hw", "convT_wide", "pdl", "pdl_tensor_trigger".
+ * These are PROCESS-GLOBAL and not synchronised: they are the one exception to "no global state except the error
+ * string" — set them before the first launch (or between launches of a single-threaded test), never concurrently
+ * with launches from another thread.  Production code does not call this function. */
 int clk_set_tuning(const char* key, int value);
 
 /* ---- layout (trainer.py:168 inputs.to(device); models/unet.py:74 forward input/output) ---- */
@@ -159,16 +166,6 @@ int clk_bn_apply_pool(const void* y, void* z, void* pooled, void* idx, const flo
                       const float* shift, int N, int H, int W, int C, clk_stream_t st);
 /* Fused-finalize forms used by the step (one launch instead of two): the per-channel coefficients are computed
  * from the raw sums in the kernel prologue; block 0 writes mean / invstd / running stats (resp. dgamma / dbeta). */
-int clk_bn_apply_fused(const void* y, void* z, const double* sum, const double* sq, const float* gamma,
-                       const float* beta, float* running_mean, float* running_var, float* mean_out, float* invstd_out,
-                       long long P, int C, double count, float eps, float momentum, int training, clk_stream_t st);
-int clk_bn_apply_pool_fused(const void* y, void* z, void* pooled, void* idx, const double* sum, const double* sq,
-                            const float* gamma, const float* beta, float* running_mean, float* running_var,
-                            float* mean_out, float* invstd_out, int N, int H, int W, int C, double count, float eps,
-                            float momentum, int training, clk_stream_t st);
-int clk_bn_relu_bwd_apply_fused(const void* dz, const void* y, void* dpre, const double* s1, const double* s2,
-                                const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
-                                double* dbias, long long P, int C, double count, int training, clk_stream_t st);
 /* din = scatter(dpooled by idx) + skip (skip may be NULL): max-pool backward fused with the
  * skip-connection gradient sum. */
 int clk_maxpool_bwd_add(const void* dpooled, const void* idx, const void* skip, void* din, int N, int H,

@@ -35,7 +35,7 @@ def time_cfg(flags, tune, steps=40):
 
 
 if __name__ == "__main__":
-    base = dict(use_side_stream=True, fuse_bn=False, side_pack=True)
+    base = dict(use_side_stream=True, side_pack=True)
     nos = dict(use_side_stream=False, side_pack=False)
     nos = dict(use_side_stream=False, side_pack=False)
     nos = dict(use_side_stream=False, side_pack=False)
@@ -43,7 +43,7 @@ if __name__ == "__main__":
                 ("one stream", nos, {}), ("default", {}, {})]
     if "--all" in sys.argv:
         sys.argv.remove("--all")
-        variants += [("fuse_bn", dict(fuse_bn=True), {"pdl": 1}), ("no side_pack", dict(side_pack=False), {}),
+        variants += [("no side_pack", dict(side_pack=False), {}),
                      ("fprop_bn=64", {}, {"fprop_bn": 64}), ("conv3 generic only", {}, {"fprop_bn": 0, "conv3_v2": 0}),
                      ("conv3 halo 1-CTA everywhere", {}, {"conv3_v2": 2, "conv3_pair": 0}),
                      ("wgrad 1-CTA halo", {}, {"conv3_v2": 4, "conv3_pair": 1, "wgrad_v2": 1}),

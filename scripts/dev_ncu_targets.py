@@ -138,6 +138,63 @@ def main():
         la = torch.zeros(2, device=dev, dtype=torch.float64)
         return lambda: ops.head_loss_bwd(z, wf, wd, b, y, 21, dz=dz, dw=dw, dbias=db, loss_acc=la)
 
+    # ---- HBM-bound kernels of the statistics / loss / input paths at the config-2 / config-5 sizes (16 x 256 x 256)
+    @case("confusion")
+    def _():
+        tgt = torch.randint(0, 21, (B, S, S), device=dev)
+        prd = torch.randint(0, 21, (B, S, S), device=dev)
+        conf = torch.zeros(21 * 21, device=dev, dtype=torch.int64)
+        return lambda: ops.confusion_matrix(tgt, prd, 21, conf=conf)
+
+    @case("argmax_confusion")
+    def _():
+        lg = torch.randn(B, S, S, 21, device=dev)
+        y = torch.randint(0, 21, (B, S, S), device=dev)
+        conf = torch.zeros(22 * 22, device=dev, dtype=torch.int64)
+        ok = torch.zeros(1, device=dev, dtype=torch.int64)
+        return lambda: ops.argmax_confusion(lg, y, nc=22, want_pred=True, conf=conf, correct=ok)
+
+    @case("head_argmax")
+    def _():
+        z = t(B, S, S, 64)
+        wf = t(32, 64)
+        b = torch.zeros(21, device=dev)
+        y = torch.randint(0, 21, (B, S, S), device=dev)
+        conf = torch.zeros(21 * 21, device=dev, dtype=torch.int64)
+        ok = torch.zeros(1, device=dev, dtype=torch.int64)
+        return lambda: ops.head_argmax_confusion(z, wf, b, y, 21, nc=21, conf=conf, correct=ok)
+
+    @case("ce_kd_loss")
+    def _():
+        lg = torch.randn(B, S, S, 21, device=dev)
+        old = torch.randn(B, S, S, 16, device=dev)
+        y = torch.randint(0, 21, (B, S, S), device=dev)
+        dl = torch.zeros(B, S, S, 64, device=dev, dtype=bf16)
+        la = torch.zeros(2, device=dev, dtype=torch.float64)
+        return lambda: ops.ce_kd_loss(lg, y, old, T=2.0, lam=1.0, dlogits=dl, loss_acc=la)
+
+    @case("maxpool_bwd")
+    def _():
+        dp = t(B, S // 2, S // 2, 64)
+        skip, yy = t(B, S, S, 64), t(B, S, S, 64)
+        idx = torch.randint(0, 4, (B, S // 2, S // 2, 64), device=dev, dtype=torch.uint8)
+        s1 = torch.zeros(64, device=dev, dtype=torch.float64)
+        out = torch.empty_like(skip)
+        return lambda: ops.maxpool_bwd_add_reduce(dp, idx, skip, yy, s1, s1.clone(), out=out)
+
+    @case("im2col_stem")
+    def _():
+        x = torch.randn(B, 3, S, S, device=dev)
+        return lambda: ops.im2col_stem(x)
+
+    @case("adam")
+    def _():
+        import continual_learning_b200 as clk
+        ps = [torch.nn.Parameter(torch.randn(31_044_821, device=dev))]
+        ps[0].grad = torch.randn_like(ps[0])
+        opt = clk.FusedAdam(ps, lr=1e-4, betas=(0.5, 0.99))
+        return lambda: opt.step()
+
     for name, make in cases.items():
         if want and name not in want:
             continue
