@@ -24,6 +24,7 @@ int g_wgrad_ctas = 0;         // generic wgrad: total CTAs aimed at by the split
 int g_wgrad_bn = 64;
 int g_wgrad_v2 = 2;          // conv3x3 wgrad: 0 generic, 1 halo (1 CTA), 2 CTA-pair halo where Cout % 128 == 0 (default)
 int g_conv3_v2 = 4;          // conv3x3 fprop/dgrad kernel: 0 generic, 1 hybrid, 2 halo (1 CTA), 4 CTA-pair halo (default)
+int g_tma_store = 1;         // generic GEMM kernel: bf16 output through shared-memory staging + TMA tensor stores
 int g_conv3_rowtap = 1;      // 64-output-channel conv3x3 forward / dgrad on the row-tap kernel (N = 192), K <= 128
 int g_conv3_pair = 1;        // CTA-pair kernel (cta_group::2, BN = 256) whenever the N extent is a multiple of 256
 int g_conv3_min_hw = 2048;  // halo kernel for images with at least this many pixels; smaller maps use the generic kernel (BN up to 256)
@@ -238,6 +239,7 @@ int clk_set_tuning(const char* key, int value) {
   else if (strcmp(key, "conv3_min_hw") == 0) g_conv3_min_hw = value;
   else if (strcmp(key, "conv3_pair") == 0) g_conv3_pair = value;
   else if (strcmp(key, "conv3_rowtap") == 0) g_conv3_rowtap = value;
+  else if (strcmp(key, "tma_store") == 0) g_tma_store = value;
   else if (strcmp(key, "pdl") == 0) g_pdl = value ? 1 : 0;
   else if (strcmp(key, "convT_wide") == 0) g_convT_wide = value ? 1 : 0;
   else if (strcmp(key, "pdl_tensor_trigger") == 0) return cuda_status(igemm_set_pdl_mode(value), "pdl_tensor_trigger");
@@ -670,6 +672,12 @@ static int gemm_fprop_impl(const void* a, int K, const void* w, const float* bia
   CUtensorMap a0, b;
   CHECK_RC(map_linear(&a0, a, P, K, 128));
   CHECK_RC(map_weights(&b, w, 1, Npad, K, BN));
+  if (g_tma_store && !out_is_f32 && n_store % 64 == 0 && ldo % 8 == 0) {
+    CUtensorMap o;
+    CHECK_RC(map_linear(&o, out, P, ldo, 128));
+    p.tma_store = 1;
+    return cuda_status(launch_fprop(BN, 0, a0, a0, b, p, num_tiles(p.g), Npad / BN, S(st), &o), "gemm_fprop");
+  }
   return cuda_status(launch_fprop(BN, out_is_f32, a0, a0, b, p, num_tiles(p.g), Npad / BN, S(st)), "gemm_fprop");
 }
 
@@ -737,6 +745,15 @@ int clk_convT2x2_fprop(const void* x, const void* w, const float* bias, void* y,
   CUtensorMap a0, b;
   CHECK_RC(map_linear(&a0, x, P, Cin, 128));
   CHECK_RC(map_weights(&b, w, 1, 4 * Cout, Cin, BN));
+  if (g_tma_store && (W % 128 == 0 || 128 % W == 0)) {
+    // a tile = 128 consecutive input pixels = a [th][tw] block of the merged [N*H][W] grid: one TMA store per
+    // 64-column group through the quadrant view {C, 2, W, 2, N*H} of y
+    const int tw = W < 128 ? W : 128;
+    CUtensorMap o;
+    CHECK_RC(map_quad(&o, y, N, H, W, Cout, tw, 128 / tw));
+    p.tma_store = 2;
+    return cuda_status(launch_fprop(BN, 0, a0, a0, b, p, num_tiles(p.g), 4 * Cout / BN, S(st), &o), "convT2x2_fprop");
+  }
   return cuda_status(launch_fprop(BN, 0, a0, a0, b, p, num_tiles(p.g), 4 * Cout / BN, S(st)), "convT2x2_fprop");
 }
 
@@ -757,6 +774,12 @@ int clk_convT2x2_dgrad(const void* dy, const void* wd, void* dx, int N, int H, i
   CUtensorMap a0, b;
   CHECK_RC(map_quad(&a0, dy, N, H, W, Cout, p.g.tw, p.g.th));
   CHECK_RC(map_weights(&b, wd, 4, Cin, Cout, BN));
+  if (g_tma_store) {
+    CUtensorMap o;
+    CHECK_RC(map_rows(&o, dx, N, H, W, Cin, p.g.tw, p.g.th));
+    p.tma_store = 3;
+    return cuda_status(launch_fprop(BN, 0, a0, a0, b, p, num_tiles(p.g), Cin / BN, S(st), &o), "convT2x2_dgrad");
+  }
   return cuda_status(launch_fprop(BN, 0, a0, a0, b, p, num_tiles(p.g), Cin / BN, S(st)), "convT2x2_dgrad");
 }
 

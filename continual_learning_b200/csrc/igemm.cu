@@ -98,7 +98,7 @@ template <int BN, int STAGES, typename OutT>
 __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
     igemm_fprop_kernel(const __grid_constant__ CUtensorMap mapA0,
                        const __grid_constant__ CUtensorMap mapA1,
-                       const __grid_constant__ CUtensorMap mapB,
+                       const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapO,
                        const __grid_constant__ FpropParams p, const int m_tiles, const int n_tiles) {
   constexpr int A_BYTES = 128 * 128;
   constexpr int B_BYTES = BN * 128;
@@ -212,6 +212,9 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
     const bool do_stats = p.stat_sum != nullptr;
     const bool affine = p.bn_scale != nullptr;
     float* scratch = scratch_all + (warp - 2) * (32 * 33);
+    uint8_t* stage_base = reinterpret_cast<uint8_t*>(scratch_all);  // two 16 KB staging tiles (TMA-store path)
+    const bool tma_out = sizeof(OutT) == 2 && p.tma_store != 0;
+    uint32_t nst = 0;  // staged 64-column groups so far (buffer parity)
     uint32_t itile = 0;
     int bias_nt = -1;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++itile) {
@@ -286,7 +289,37 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
           uint32_t pk[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-          if (valid && (n0 + chunk * 32) < p.n_store) {
+          if (tma_out) {
+            // 64-column group i = chunk / 2: the two warps of a quadrant hold its two 32-column halves.  Stage the
+            // [128 rows][128 B] tile in the SWIZZLE_128B pattern of the store map (conflict-free), then ONE TMA store
+            // per group writes full lines: the per-thread stores below cost 32 LSU wave fronts per instruction
+            // (one 16-byte piece per pixel row) and bound the short-K GEMMs (ConvTranspose2d, stem).
+            uint8_t* sbuf = stage_base + (nst & 1) * 16384;
+            if (etid == 0) tma_store_wait_read<1>();  // the store two groups back has read this buffer
+            named_bar_sync(3, kFpEpiThreads);
+            uint8_t* rp = sbuf + m * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(rp + ((((chunk & 1) * 4 + j) ^ (m & 7)) << 4)) =
+                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+            fence_proxy_async();
+            named_bar_sync(3, kFpEpiThreads);
+            const int gcol = n0 + (chunk >> 1) * 64;
+            if (etid == 0 && gcol < p.n_store) {
+              if (p.tma_store == 1) {
+                tma_store_5d(&mapO, sbuf, gcol, b1, 0, 0, 0);
+              } else if (p.tma_store == 2) {
+                // the tile is 128 consecutive input pixels (raster order): rows b1 / W.., columns b1 % W.. of the
+                // merged [N*H][W] grid; quadrant qd = (i, j) selects the output pixel (2h + i, 2w + j)
+                const int qd = gcol / p.cout_q;
+                tma_store_5d(&mapO, sbuf, gcol - qd * p.cout_q, qd & 1, b1 % p.g.W, qd >> 1, b1 / p.g.W);
+              } else {
+                tma_store_5d(&mapO, sbuf, gcol, b2, b4, 0, 0);
+              }
+              tma_store_commit();
+            }
+            ++nst;
+          } else if (valid && (n0 + chunk * 32) < p.n_store) {
             OutT* crow = drow + chunk * 32;
             if (shuffle_chunks) {
               const int gcol = n0 + chunk * 32;
@@ -347,6 +380,7 @@ __global__ void __launch_bounds__(kFpThreads, (BN <= 64 ? 2 : 1))
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
+    if (tma_out && etid == 0) tma_store_wait<0>();
     // statistics stay in shared memory across the tiles of one N tile: one fp64 atomic per channel per CTA and N tile
     if (do_stats && bias_nt >= 0) {
       named_bar_sync(1, kFpEpiThreads);
@@ -1846,7 +1880,7 @@ static constexpr int fprop_smem_bytes() {
 
 template <int BN, int STAGES, typename OutT>
 static cudaError_t launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1,
-                                  const CUtensorMap& b, const FpropParams& p, int m_tiles,
+                                  const CUtensorMap& b, const CUtensorMap& o, const FpropParams& p, int m_tiles,
                                   int n_tiles, cudaStream_t st) {
   constexpr int smem = fprop_smem_bytes<BN, STAGES>();
   static PerDeviceOnce attr_once;
@@ -1858,21 +1892,24 @@ static cudaError_t launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1,
   int grid = m_tiles * n_tiles;
   const int cap = g_fprop_sms * (smem <= 113 * 1024 ? 2 : 1);  // resident CTAs per SM by shared memory
   if (grid > cap) grid = cap;
-  launch_k(igemm_fprop_kernel<BN, STAGES, OutT>, dim3(grid), dim3(kFpThreads), smem, st, a0, a1, b, p, m_tiles, n_tiles);
+  launch_k(igemm_fprop_kernel<BN, STAGES, OutT>, dim3(grid), dim3(kFpThreads), smem, st, a0, a1, b, o, p, m_tiles, n_tiles);
   return cudaGetLastError();
 }
 
 cudaError_t launch_fprop(int BN, int out_is_f32, const CUtensorMap& a0, const CUtensorMap& a1,
                          const CUtensorMap& b, const FpropParams& p, int m_tiles, int n_tiles,
-                         cudaStream_t st) {
+                         cudaStream_t st, const CUtensorMap* o) {
+  if ((p.tma_store != 0) != (o != nullptr)) return cudaErrorInvalidValue;
+  if (p.tma_store != 0 && (out_is_f32 || p.n_store % 64 != 0 || p.split_c != 0)) return cudaErrorInvalidValue;
+  const CUtensorMap& om = o != nullptr ? *o : a0;  // unused unless p.tma_store
   if (out_is_f32) {
-    if (BN == 32) return launch_fprop_t<32, 4, float>(a0, a1, b, p, m_tiles, n_tiles, st);
+    if (BN == 32) return launch_fprop_t<32, 4, float>(a0, a1, b, om, p, m_tiles, n_tiles, st);
     return cudaErrorInvalidValue;
   }
   switch (BN) {
-    case 64: return launch_fprop_t<64, 3, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
-    case 128: return launch_fprop_t<128, 3, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
-    case 256: return launch_fprop_t<256, 3, __nv_bfloat16>(a0, a1, b, p, m_tiles, n_tiles, st);
+    case 64: return launch_fprop_t<64, 3, __nv_bfloat16>(a0, a1, b, om, p, m_tiles, n_tiles, st);
+    case 128: return launch_fprop_t<128, 3, __nv_bfloat16>(a0, a1, b, om, p, m_tiles, n_tiles, st);
+    case 256: return launch_fprop_t<256, 3, __nv_bfloat16>(a0, a1, b, om, p, m_tiles, n_tiles, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -50,6 +50,11 @@ struct FpropParams {
   double* stat_sq;
   const float* bn_scale;  // inference: out = relu(acc + bias) * bn_scale + bn_shift (stat_* must then be null)
   const float* bn_shift;
+  // bf16 output through shared-memory staging + TMA tensor stores (full 128-byte lines, clipped at the tensor border)
+  // instead of per-thread 16-byte stores at a >= 128-byte stride.  0 = off; 1 = ADDR_LINEAR rows map {C, P};
+  // 2 = ConvTranspose2d pixel shuffle through the quadrant map {C, 2, 2W.., 2, N*H} of the output (nb == 1, H % th == 0);
+  // 3 = ADDR_QUAD geometry, plain rows map {C, W, N*H}.  Needs n_store % 64 == 0 and a single destination.
+  int tma_store;
 };
 
 struct WgradParams {
@@ -72,7 +77,7 @@ cudaError_t igemm_set_pdl_mode(int mode);
 // Launchers (igemm.cu). Return cudaError_t from the launch; maps are built by the caller.
 cudaError_t launch_fprop(int BN, int out_is_f32, const CUtensorMap& a0, const CUtensorMap& a1,
                          const CUtensorMap& b, const FpropParams& p, int m_tiles, int n_tiles,
-                         cudaStream_t st);
+                         cudaStream_t st, const CUtensorMap* o = nullptr);
 cudaError_t launch_wgrad(int BN, const CUtensorMap& u, const CUtensorMap& t0, const CUtensorMap& t1,
                          const WgradParams& p, cudaStream_t st);
 
