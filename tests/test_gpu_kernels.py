@@ -126,7 +126,11 @@ def test_gemm_fprop_eval_stem(ops):
 
 
 @pytest.mark.parametrize("n,h,w,c0,c1,co", [(2, 16, 16, 64, 0, 64), (2, 8, 8, 128, 128, 128), (1, 16, 16, 256, 0, 64),
-                                              (2, 6, 10, 64, 64, 64), (1, 64, 48, 128, 0, 64), (2, 33, 17, 64, 64, 128)])
+                                              (2, 6, 10, 64, 64, 64), (1, 64, 48, 128, 0, 64), (2, 33, 17, 64, 64, 128),
+                                              # 64 gradient channels out of 64 / 128 in: the paired-tap kernel (one and
+                                              # two K chunks), widths that are not multiples of its 30-pixel segments
+                                              (2, 6, 10, 64, 0, 128), (1, 33, 61, 64, 0, 128), (3, 9, 31, 64, 0, 64),
+                                              (1, 1, 1, 64, 0, 64)])
 def test_conv3x3_dgrad_split_destinations(ops, conv_kernel, n, h, w, c0, c1, co):
     g = gen(7 + n + h + co)
     dy, wt = bfr(rnd(g, n, co, h, w)), rnd(g, co, c0 + c1, 3, 3, scale=0.05)
