@@ -10,7 +10,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libclk.so")
+LIB_PATH = os.environ.get("CLK_LIB_PATH") or os.path.join(_HERE, "libclk.so")  # CLK_LIB_PATH: developer A/B of two builds
 
 CLK_OK = 0
 _ERRNAMES = {-1: "CLK_E_BADARG", -2: "CLK_E_UNSUPPORTED_SHAPE", -3: "CLK_E_WORKSPACE", -4: "CLK_E_CUDA",

@@ -50,11 +50,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
-#ifdef CLK_TEST_WAIT
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-#endif
       "selp.b32 %0, 1, 0, p;\n\t"
       "}\n"
       : "=r"(ok)
