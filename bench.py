@@ -233,7 +233,7 @@ def run_b200(args):
     model.train()
     opt = clk.FusedAdam(model.parameters(), lr=1e-4, betas=(0.5, 0.99))  # trainer.py:108-110, main.py:77-80
     comm = None
-    if world > 1:
+    if world > 1 or os.environ.get("CLK_FORCE_SEGMENTS"):  # (developer probe: the four-graph schedule on one GPU)
         names = [k for k, _ in model.named_parameters()]
         comm = parallel.GradAllReduce([p.numel() for p in model.parameters()], names)
     old_model = None
