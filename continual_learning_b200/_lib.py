@@ -30,6 +30,7 @@ SIGNATURES = {
     "clk_nchw_f32_to_nhwc_bf16": [p, p, i, i, i, i, i, p],
     "clk_nhwc_to_nchw_f32": [p, i, p, i, i, i, i, i, p],
     "clk_im2col3x3_stem": [p, p, i, i, i, i, p],
+    "clk_stem_conv3x3_fprop": [p, i, p, p, p, p, p, p, p, i, i, i, i, p],
     "clk_pack_w": [p, p, p, i, i, i, i, i, i, i, i, p],
     "clk_unpack_wgrad": [p, p, i, i, i, i, i, f, i, i, p],
     "clk_pack_w_multi": [p, i, i, i, p],

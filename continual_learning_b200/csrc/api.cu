@@ -681,6 +681,22 @@ static int gemm_fprop_impl(const void* a, int K, const void* w, const float* bia
   return cuda_status(launch_fprop(BN, out_is_f32, a0, a0, b, p, num_tiles(p.g), Npad / BN, S(st)), "gemm_fprop");
 }
 
+int clk_stem_conv3x3_fprop(const float* x, int Cin, const void* w, const float* bias, void* y, double* stat_sum,
+                           double* stat_sq, const float* bn_scale, const float* bn_shift, int N, int H, int W, int relu,
+                           clk_stream_t st) {
+  if (!x || !w || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0) return fail(CLK_E_BADARG, "stem_conv3x3_fprop: bad args");
+  if ((bn_scale == nullptr) != (bn_shift == nullptr) || (bn_scale && stat_sum) || (stat_sum == nullptr) != (stat_sq == nullptr))
+    return fail(CLK_E_BADARG, "stem_conv3x3_fprop: scale and shift come together and exclude the statistics");
+  if (Cin * 9 > 32 || H % 8 || W % 16)
+    return fail(CLK_E_UNSUPPORTED_SHAPE, "stem_conv3x3_fprop: needs Cin*9 <= 32, H %% 8 == 0, W %% 16 == 0 (Cin=%d H=%d W=%d); "
+                "use clk_im2col3x3_stem + clk_gemm_fprop", Cin, H, W);
+  CUtensorMap mw, mo;
+  CHECK_RC(map_weights(&mw, w, 1, 64, 64, 64));
+  CHECK_RC(map_nhwc(&mo, y, N, H, W, 64, 16, 8, 1));
+  return cuda_status(launch_stem_conv(mw, mo, x, N, Cin, H, W, bias, relu, stat_sum, stat_sq, bn_scale, bn_shift,
+                                      g_num_sms_api, S(st)), "stem_conv3x3_fprop");
+}
+
 int clk_gemm_fprop(const void* a, int K, const void* w, const float* bias, void* out, int ldo, int n_store,
                    int out_is_f32, int relu, double* stat_sum, double* stat_sq, long long P, int Npad,
                    clk_stream_t st) {

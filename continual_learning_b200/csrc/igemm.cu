@@ -1872,6 +1872,320 @@ cudaError_t launch_conv3r(const CUtensorMap& a0, const CUtensorMap& a1, const CU
 }
 
 // ------------------------------------------------------------------------------------------
+// STEM (enc1.0, models/unet.py:50): conv3x3 of the 3-channel fp32 NCHW input, Cout = 64, as ONE kernel.  Round 1 wrote a
+// K = 64 im2col matrix (134 MB at 16 x 256 x 256), read it back in a generic GEMM launch: ~7x the algorithmic bytes.
+// Here 8 builder warps assemble the im2col tile [128 pixels][k = c*9 + r*3 + s, 27 of 32 used] directly in shared memory
+// in the SWIZZLE_128B K-major layout the tensor core reads (from a 3 x 10 x 18 fp32 input patch staged per tile, zero
+// outside the image = the conv padding), two K = 16 MMAs (M = 128, N = 64) multiply it with the resident [64][64]
+// weight tile, and 4 epilogue warps do bias + ReLU (+ inference BatchNorm), stage the bf16 tile and write it with one
+// TMA tensor store; BatchNorm statistics are summed from the staged tile.  Algorithmic bytes: 12 B in + 128 B out per
+// pixel.  Tile = 8 image rows x 16 pixels (H % 8 == 0, W % 16 == 0: the U-Net needs multiples of 16 anyway).
+constexpr int kStBuild = 128;                       // builder threads (warps 2..5): one im2col row (pixel) each
+constexpr int kStEpi = 256;                         // epilogue threads (warps 6..13): (TMEM quadrant, 32-column half)
+constexpr int kStThreads = 64 + kStBuild + kStEpi;  // + warp 0 (weights TMA), warp 1 (TMEM alloc + MMA issue)
+constexpr int kStPatch = 3 * 10 * 18;               // fp32 input patch of one tile
+constexpr int kStSmem = 2 * 16384 /*A*/ + 8192 /*W*/ + 2 * 16384 /*out staging*/ + 2 * kStPatch * 4 + 3 * 64 * 4 + 128 * 8 + 9 * 8 + 16 + 1024;
+
+struct StemParams {
+  const float* x;  // [N][Cin][H][W] fp32
+  int N, Cin, H, W;
+  int tiles_w, tiles_h, total;
+  const float* bias;
+  int relu;
+  double* stat_sum;
+  double* stat_sq;
+  const float* bn_scale;
+  const float* bn_shift;
+};
+
+__global__ void __launch_bounds__(kStThreads, 2)
+    stem_conv_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapO,
+                     const __grid_constant__ StemParams p) {
+  if (d_pdl_mode == 0) pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint8_t* sA = smem;                    // 2 x [128 px][128 B]
+  uint8_t* sW = smem + 2 * 16384;        // [64 cout][128 B]
+  uint8_t* sO = sW + 8192;               // 2 x [128 px][128 B]
+  float* s_patch = reinterpret_cast<float*>(sO + 2 * 16384);  // 2 x [3][10][18]
+  float* s_bias = s_patch + 2 * kStPatch;
+  float* s_sum = s_bias + 64;
+  float* s_sq = s_sum + 64;
+  double* s_dstat = reinterpret_cast<double*>(s_sq + 64);  // [2][64] per-CTA statistics (fp64)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(s_dstat + 128);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* acc_full = a_empty + 2;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* w_full = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool affine = p.bn_scale != nullptr;
+  const bool do_stats = p.stat_sum != nullptr;
+  for (int i = tid; i < 128; i += kStThreads) s_dstat[i] = 0.0;
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], kStBuild / 32);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], kStEpi / 32);
+    }
+    mbar_init(w_full, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&mapW);
+    tma_prefetch_desc(&mapO);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 128);  // 2 accumulator stages x 64 columns
+    tmem_relinquish();
+  }
+  // the unused half of every im2col row (k = 32..63) is zero for good; bias / inference-affine slots
+  for (int i = tid; i < 256; i += kStThreads) {
+    uint4* row = reinterpret_cast<uint4*>(sA + i * 128);
+#pragma unroll
+    for (int c = 4; c < 8; ++c) row[c ^ (i & 7)] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  for (int i = tid; i < 64; i += kStThreads) {
+    s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.f;
+    s_sum[i] = affine ? p.bn_scale[i] : 0.f;
+    s_sq[i] = affine ? p.bn_shift[i] : 0.f;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_full, 8192);
+      tma_load_3d(sW, &mapW, w_full, 0, 0, 0);
+    }
+    __syncwarp();
+    if (d_pdl_mode == 1) pdl_launch_dependents();
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+      mbar_wait(w_full, 0);
+      tc_fence_after();
+      const uint64_t bdesc = umma_smem_desc(smem_u32(sW), 16, 1024);
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
+        const uint32_t b = it & 1, ph = (it >> 1) & 1;
+        mbar_wait(&acc_empty[b], ph ^ 1);
+        mbar_wait(&a_full[b], ph);
+        tc_fence_after();
+        const uint64_t adesc = umma_smem_desc(smem_u32(sA + b * 16384), 16, 1024);
+        umma_bf16(tmem_base + b * 64, adesc, bdesc, idesc, 0u);
+        umma_bf16(tmem_base + b * 64, adesc + 2, bdesc + 2, idesc, 1u);  // k = 16..31 (+32 bytes)
+        umma_commit(&a_empty[b]);
+        umma_commit(&acc_full[b]);
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // ------------------------------------------------ builders: im2col tile from the fp32 NCHW input, thread = pixel
+    const int m = tid - 64;  // 0..127: pixel (m / 16, m % 16) of the tile
+    const int pbase = (m >> 4) * 18 + (m & 15);
+    // the (channel, row, column) of the up to five patch elements this thread stages per tile
+    int pc[5], pr[5], pcol[5];
+#pragma unroll
+    for (int e = 0; e < 5; ++e) {
+      const int i = m + e * kStBuild;
+      pc[e] = i / 180;
+      pr[e] = (i - pc[e] * 180) / 18;
+      pcol[e] = i - pc[e] * 180 - pr[e] * 18;
+      if (i >= p.Cin * 180) pc[e] = -1;
+    }
+    const long long plane = static_cast<long long>(p.H) * p.W;
+    // the patch values of a tile are requested one tile ahead (registers), so the global-load latency overlaps the
+    // assembly of the previous tile
+    auto load_patch = [&](int t, float (&pv)[5]) {
+      const int tx = t % p.tiles_w;
+      const int rr = t / p.tiles_w;
+      const int ty = rr % p.tiles_h;
+      const int n = rr / p.tiles_h;
+      const int h0 = ty * 8 - 1, w0 = tx * 16 - 1;
+      const float* xn = p.x + static_cast<long long>(n) * p.Cin * plane;
+#pragma unroll
+      for (int e = 0; e < 5; ++e) {
+        const int hh = h0 + pr[e], ww = w0 + pcol[e];
+        pv[e] = 0.f;
+        if (pc[e] >= 0 && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) pv[e] = __ldg(xn + pc[e] * plane + hh * p.W + ww);
+      }
+    };
+    float pv[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (static_cast<int>(blockIdx.x) < p.total) load_patch(blockIdx.x, pv);
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
+      const uint32_t b = it & 1, ph = (it >> 1) & 1;
+      float* patch = s_patch + b * kStPatch;
+      // (this patch buffer was last read two tiles ago, before the builders' previous barrier)
+#pragma unroll
+      for (int e = 0; e < 5; ++e)
+        if (pc[e] >= 0) patch[m + e * kStBuild] = pv[e];
+      named_bar_sync(4, kStBuild);
+      if (t + static_cast<int>(gridDim.x) < p.total) load_patch(t + gridDim.x, pv);
+      // im2col row of this pixel: k = c*9 + r*3 + s, 27 of 32 columns used (compile-time offsets into the patch)
+      uint32_t pk[16];
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        float v[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int k = 2 * jj + e;
+          const int c = k / 9, rs = k - c * 9;
+          const int r = rs / 3, s2 = rs - r * 3;
+          v[e] = (k < 27 && c < p.Cin) ? patch[pbase + c * 180 + r * 18 + s2] : 0.f;
+        }
+        pk[jj] = pack_bf16x2(v[0], v[1]);
+      }
+      mbar_wait(&a_empty[b], ph ^ 1);  // the MMAs of tile it - 2 are done with this buffer
+      uint4* row = reinterpret_cast<uint4*>(sA + b * 16384 + m * 128);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) row[c ^ (m & 7)] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[b]);
+    }
+  } else {
+    // ------------------------------------------------ epilogue: 8 warps = (TMEM lane quadrant q, 32-column half)
+    const int q = warp & 3;
+    const int half = (warp - 6) >> 2;
+    const int etid = tid - 64 - kStBuild;  // 0..255
+    const int m = q * 32 + lane;
+    const int st_cc = etid & 7, st_row0 = etid >> 3;  // statistics: 16-byte chunk column, rows st_row0 + 32 i
+    double st_s[8], st_q[8];  // fp64 totals: ~220 values per accumulator and CTA at 16 x 256 x 256
+    float ts[8], tq[8];       // fp32 partials of up to 8 tiles
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      st_s[j] = 0.0;
+      st_q[j] = 0.0;
+      ts[j] = 0.f;
+      tq[j] = 0.f;
+    }
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
+      const uint32_t b = it & 1, ph = (it >> 1) & 1;
+      const int tx = t % p.tiles_w;
+      const int rr = t / p.tiles_w;
+      const int ty = rr % p.tiles_h;
+      const int n = rr / p.tiles_h;
+      uint8_t* sbuf = sO + b * 16384;
+      mbar_wait(&acc_full[b], ph);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * 64 + half * 32, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);  // the accumulator stage is in registers
+      uint32_t pk[16];
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        float x[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = half * 32 + 2 * jj + e;
+          float f = __uint_as_float(v[2 * jj + e]) + s_bias[j];
+          if (p.relu) f = fmaxf(f, 0.f);
+          if (affine) f = fmaf(f, s_sum[j], s_sq[j]);
+          x[e] = f;
+        }
+        pk[jj] = pack_bf16x2(x[0], x[1]);
+      }
+      if (etid == 0) tma_store_wait_read<1>();  // the store two tiles back has read this staging buffer
+      named_bar_sync(5, kStEpi);
+      uint8_t* rp = sbuf + m * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        *reinterpret_cast<uint4*>(rp + (((half * 4 + c) ^ (m & 7)) << 4)) =
+            make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      fence_proxy_async();
+      named_bar_sync(5, kStEpi);
+      if (etid == 0) {
+        tma_store_5d(&mapO, sbuf, 0, tx * 16, ty * 8, n, 0);
+        tma_store_commit();
+      }
+      if (do_stats) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = st_row0 + 32 * i;
+          const uint4 u4 = *reinterpret_cast<const uint4*>(sbuf + row * 128 + ((st_cc ^ (row & 7)) << 4));
+          const uint32_t u[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float lo = bf16lo_to_f32(u[jj]), hi = bf16hi_to_f32(u[jj]);
+            ts[2 * jj] += lo;
+            ts[2 * jj + 1] += hi;
+            tq[2 * jj] = fmaf(lo, lo, tq[2 * jj]);
+            tq[2 * jj + 1] = fmaf(hi, hi, tq[2 * jj + 1]);
+          }
+        }
+        if ((it & 7) == 7) {  // fp32 partials over 8 tiles (32 values), then into the fp64 totals
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            st_s[j] += static_cast<double>(ts[j]);
+            st_q[j] += static_cast<double>(tq[j]);
+            ts[j] = 0.f;
+            tq[j] = 0.f;
+          }
+        }
+      }
+    }
+    if (etid == 0) tma_store_wait<0>();
+    if (do_stats) {
+      // lanes l, l + 8, l + 16, l + 24 hold the same chunk column; then ONE fp64 atomic per channel and warp
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        st_s[j] += static_cast<double>(ts[j]);
+        st_q[j] += static_cast<double>(tq[j]);
+        st_s[j] += __shfl_xor_sync(0xffffffffu, st_s[j], 8);
+        st_s[j] += __shfl_xor_sync(0xffffffffu, st_s[j], 16);
+        st_q[j] += __shfl_xor_sync(0xffffffffu, st_q[j], 8);
+        st_q[j] += __shfl_xor_sync(0xffffffffu, st_q[j], 16);
+      }
+      // the 8 warps meet in shared memory, then ONE fp64 atomic per channel and CTA (2 x 64 hot addresses chip-wide)
+      if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          atomicAdd(&s_dstat[lane * 8 + j], st_s[j]);
+          atomicAdd(&s_dstat[64 + lane * 8 + j], st_q[j]);
+        }
+      }
+      named_bar_sync(5, kStEpi);
+      if (etid < 64) atomicAdd(&p.stat_sum[etid], s_dstat[etid]);
+      else if (etid < 128) atomicAdd(&p.stat_sq[etid - 64], s_dstat[etid]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+// w box {64, 64, 1} of the packed stem weights [64 cout][64 k]; o = NHWC map of y [N][H][W][64], box {64, 16, 8, 1, 1}
+cudaError_t launch_stem_conv(const CUtensorMap& w, const CUtensorMap& o, const float* x, int N, int Cin, int H, int W,
+                             const float* bias, int relu, double* stat_sum, double* stat_sq, const float* bn_scale,
+                             const float* bn_shift, int num_sms, cudaStream_t st) {
+  if (H % 8 || W % 16 || Cin * 9 > 32) return cudaErrorInvalidValue;
+  StemParams p;
+  p.x = x; p.N = N; p.Cin = Cin; p.H = H; p.W = W;
+  p.tiles_w = W / 16; p.tiles_h = H / 8; p.total = N * p.tiles_h * p.tiles_w;
+  p.bias = bias; p.relu = relu; p.stat_sum = stat_sum; p.stat_sq = stat_sq; p.bn_scale = bn_scale; p.bn_shift = bn_shift;
+  static PerDeviceOnce attr_once;
+  if (attr_once.first()) {
+    cudaError_t e = cudaFuncSetAttribute(stem_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStSmem);
+    if (e != cudaSuccess) return e;
+  }
+  int grid = p.total < 2 * num_sms ? p.total : 2 * num_sms;  // persistent: two 448-thread CTAs per SM (76 KB, <= 72 registers)
+  launch_k(stem_conv_kernel, dim3(grid), dim3(kStThreads), kStSmem, st, w, o, p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 template <int BN, int STAGES>
 static constexpr int fprop_smem_bytes() {

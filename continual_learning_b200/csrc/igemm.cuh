@@ -129,6 +129,11 @@ cudaError_t launch_conv3r(const CUtensorMap& a0, const CUtensorMap& a1, const CU
 cudaError_t launch_conv3(int BN, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b,
                          const Conv3Params& p, int num_sms, cudaStream_t st);
 
+// direct stem conv (3-channel fp32 NCHW input -> 64 channels bf16 NHWC), see stem_conv_kernel
+cudaError_t launch_stem_conv(const CUtensorMap& w, const CUtensorMap& o, const float* x, int N, int Cin, int H, int W,
+                             const float* bias, int relu, double* stat_sum, double* stat_sq, const float* bn_scale,
+                             const float* bn_shift, int num_sms, cudaStream_t st);
+
 // fused 1x1 head + softmax cross-entropy (+ distillation) + head backward, see head_loss_kernel
 struct HeadLossParams {
   long long P;

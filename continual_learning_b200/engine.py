@@ -7,6 +7,8 @@ outputs).  Skip-connection concats (models/unet.py:83-87) are never materialised
 walk the channels of the two source tensors back to back.  fp32 master parameters stay in the
 nn.Module; bf16 packed operand copies are refreshed whenever a parameter version changes.
 """
+import os
+
 import torch
 
 from . import _lib, ops
@@ -66,6 +68,8 @@ class UNetEngine:
         self.training_fwd = True
         self.save_for_backward = True
         self.logits = None
+        self._stem_direct = False
+        self._stem_cols = None
         self.generation = 0  # bumped by every forward (stale-backward detection in unet._UNetFn)
 
     # ------------------------------------------------------------------ persistent buffers
@@ -253,6 +257,8 @@ class UNetEngine:
     # ------------------------------------------------------------------ forward
     def _unit_fwd(self, u, x0, x1, training, pool=False):
         n, h, w = x0.shape[0], x0.shape[1], x0.shape[2]
+        if u.stem and self._stem_direct:  # x0 is the fp32 NCHW input itself
+            h, w = x0.shape[2], x0.shape[3]
         u.x0, u.x1 = x0, x1
         if not training and not self.save_for_backward:
             # inference: BatchNorm with running statistics is an affine map known before the conv runs ->
@@ -262,7 +268,9 @@ class UNetEngine:
                             u.vec[0], u.vec[1], u.vec[2], u.vec[3], n * h * w, eps=bn.eps, momentum=0.0,
                             training=False)
             bias = u.conv.bias.detach()
-            if u.stem:
+            if u.stem and self._stem_direct:
+                u.z = ops.stem_conv(x0, u.wf, bias, relu=True, scale=u.vec[2], shift=u.vec[3])
+            elif u.stem:
                 u.z = ops.gemm_fprop_eval(x0, u.wf, bias, u.cout, u.vec[2], u.vec[3], relu=True)
             else:
                 u.z = ops.conv3x3_fprop_eval(x0, x1, u.wf, bias, u.vec[2], u.vec[3], relu=True)
@@ -272,7 +280,9 @@ class UNetEngine:
             return u.z
         stats = (u.s_sum, u.s_sq) if training else None
         bias = u.conv.bias.detach()
-        if u.stem:
+        if u.stem and self._stem_direct:
+            u.y = ops.stem_conv(x0, u.wf, bias, relu=True, stats=stats)  # x0 = the fp32 NCHW input itself
+        elif u.stem:
             u.y = ops.gemm_fprop(x0, u.wf, bias, u.cout, relu=True, stats=stats)
         else:
             u.y = ops.conv3x3_fprop(x0, x1, u.wf, bias, relu=True, stats=stats)
@@ -309,7 +319,17 @@ class UNetEngine:
         if training:
             self.acc_f.zero_()
         U = self.units
-        a = ops.im2col_stem(x.float())
+        # the stem runs as ONE kernel that builds its im2col tiles in shared memory; the K = 64 im2col matrix is only
+        # materialised (on the weight-gradient side stream, in the backward pass) for the stem's wgrad
+        xf = x.float().contiguous()
+        self._stem_direct = ops.stem_conv_supported(cin, h, w, U[0].cout) and os.environ.get("CLK_STEM_DIRECT", "1") != "0"
+        a = xf if self._stem_direct else ops.im2col_stem(xf)
+        self._stem_cols = None
+        if self._stem_direct and save_for_backward:
+            # the stem's weight gradient still wants the K = 64 im2col matrix: written on the side stream while the
+            # (tensor-bound) first layers run, instead of at the tail of the backward pass
+            with self._fork(xf):
+                self._stem_cols = ops.im2col_stem(xf)
         z = self._unit_fwd(U[0], a, None, training)
         self._unit_fwd(U[1], z, None, training, pool=True)
         self._join()  # packed weights of the remaining layers (side stream)
@@ -383,7 +403,8 @@ class UNetEngine:
         # this layer and the (HBM-bound) BatchNorm backward of the next one
         with self._fork(dpre):
             if u.stem:
-                ops.gemm_wgrad(dpre, u.x0, out=u.gp)
+                # (direct stem: u.x0 is the fp32 input; its im2col matrix was written during the forward pass)
+                ops.gemm_wgrad(dpre, self._stem_cols if self._stem_direct else u.x0, out=u.gp)
             else:
                 if self.deterministic:
                     ops.conv3x3_wgrad_split(dpre, u.x0, u.x1, out=u.part)
@@ -509,4 +530,5 @@ class UNetEngine:
         """drop the saved activations (after backward, or after an eval forward)."""
         for u in self.units:
             u.x0 = u.x1 = u.y = u.z = u.pooled = u.idx = None
+        self._stem_cols = None
         self.tin = []

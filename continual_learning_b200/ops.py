@@ -43,6 +43,22 @@ def im2col_stem(x):
     return a
 
 
+def stem_conv_supported(cin, h, w, cout):
+    return cin * 9 <= 32 and h % 8 == 0 and w % 16 == 0 and cout == 64
+
+
+def stem_conv(x, wf, bias, relu=True, stats=None, scale=None, shift=None, out=None):
+    """enc1.0 in one launch: x fp32 NCHW [N,Cin,H,W] -> bf16 NHWC [N,H,W,64] = relu(conv3x3(x) + bias) (+ BatchNorm
+    statistics, or * scale + shift in inference); the im2col tile only ever exists in shared memory."""
+    _dev(x)
+    n, c, h, w = x.shape
+    y = torch.empty((n, h, w, 64), device=x.device, dtype=bf16) if out is None else out
+    s_sum, s_sq = (None, None) if stats is None else stats
+    _lib.call("clk_stem_conv3x3_fprop", x.contiguous(), c, wf, bias, y, s_sum, s_sq, scale, shift, n, h, w,
+              1 if relu else 0)
+    return y
+
+
 # ------------------------------------------------------------------ weights
 def pack_conv3x3(w, out_f=None, out_d=None):
     """w fp32 [Cout,Cin,3,3] -> (fprop pack bf16 [9,Cout,Cin], dgrad pack bf16 [9,Cin,Cout] taps reversed)."""

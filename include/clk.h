@@ -54,6 +54,14 @@ int clk_nhwc_to_nchw_f32(const void* x, int x_is_f32, float* y, int N, int C, in
                          clk_stream_t st);
 /* stem im2col for the Cin<=7 first conv (models/unet.py:50): A[N*H*W][64] bf16, k = c*9+r*3+s. */
 int clk_im2col3x3_stem(const float* x_nchw, void* a, int N, int Cin, int H, int W, clk_stream_t st);
+/* the whole stem layer enc1.0 (models/unet.py:50: Conv2d(3, 64, 3, padding=1) + ReLU, + BatchNorm statistics or the
+ * inference affine) as ONE launch: the im2col tile is built in shared memory from the fp32 NCHW input, never written to
+ * HBM (12 B in + 128 B out per pixel instead of the 134 MB matrix of clk_im2col3x3_stem + clk_gemm_fprop, which remain for
+ * other shapes and for the stem's weight gradient).  x f32 [N][Cin][H][W], w = clk_pack_w'ed bf16 [64][64]
+ * (k = c*9 + r*3 + s), y bf16 NHWC [N][H][W][64].  Needs Cin*9 <= 32, H % 8 == 0, W % 16 == 0. */
+int clk_stem_conv3x3_fprop(const float* x, int Cin, const void* w, const float* bias, void* y, double* stat_sum,
+                           double* stat_sq, const float* bn_scale, const float* bn_shift, int N, int H, int W, int relu,
+                           clk_stream_t st);
 
 /* ---- weights: fp32 PyTorch layout <-> packed bf16 operand layout ----
  * src fp32 [A][B][T] (Conv2d: A=Cout,B=Cin,T=kh*kw; ConvTranspose2d: A=Cin,B=Cout,T=4)

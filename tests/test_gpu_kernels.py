@@ -467,3 +467,26 @@ def test_fused_head_argmax_confusion_equals_the_separate_ops(ops, P, c, nc):
     # accumulating form, no prediction map
     _, conf2, ok2 = ops.head_argmax_confusion(z, wf, b, y, c, nc=nc, conf=conf.clone(), correct=ok.clone())
     assert torch.equal(conf2, 2 * conf_ref) and torch.equal(ok2, 2 * ok_ref)
+
+
+@pytest.mark.parametrize("n,cin,h,w", [(2, 3, 16, 16), (1, 3, 8, 48), (3, 1, 24, 16), (2, 2, 40, 32), (16, 3, 256, 256)])
+def test_stem_conv_direct_kernel(ops, n, cin, h, w):
+    """enc1.0 (models/unet.py:50) as one launch — the im2col tile built in shared memory from the fp32 NCHW input —
+    against F.conv2d on the bf16-rounded operands, the BatchNorm statistics of its epilogue against a pass over the
+    stored tensor, the inference (affine) epilogue, and against the two-launch im2col + GEMM path it replaces."""
+    g = gen(n + h + w + cin)
+    x = rnd(g, n, cin, h, w)
+    wt, b = rnd(g, 64, cin, 3, 3, scale=0.2), rnd(g, 64)
+    wf = ops.pack_stem(wt.cuda())
+    s1, s2 = (torch.zeros(64, device="cuda", dtype=torch.float64) for _ in range(2))
+    y = ops.stem_conv(x.cuda(), wf, b.cuda(), relu=True, stats=(s1, s2))
+    ref = torch.relu(F.conv2d(bfr(x), bfr(wt), b, padding=1))
+    assert rel(from_nhwc(y), ref) <= BF16_TOL
+    yd = y.double().reshape(-1, 64)
+    assert rel(s1, yd.sum(0)) <= 1e-6 and rel(s2, (yd * yd).sum(0)) <= 1e-6
+    # same numbers as im2col + GEMM (identical bf16 operands, fp32 accumulation order aside)
+    y2 = ops.gemm_fprop(ops.im2col_stem(x.cuda()), wf, b.cuda(), 64, relu=True)
+    assert rel(y, y2) <= 1e-3
+    scale, shift = rnd(g, 64), rnd(g, 64)
+    z = ops.stem_conv(x.cuda(), wf, b.cuda(), relu=True, scale=scale.cuda(), shift=shift.cuda())
+    assert rel(from_nhwc(z), ref * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)) <= BF16_TOL
