@@ -1945,6 +1945,9 @@ __global__ void __launch_bounds__(kStThreads, 2)
 #pragma unroll
     for (int c = 4; c < 8; ++c) row[c ^ (i & 7)] = make_uint4(0u, 0u, 0u, 0u);
   }
+  // predecessor grid complete and flushed from here on: the inference scale / shift are written by the kernel right
+  // before this one (bn_finalize), so nothing that lives in global memory may be read above this line
+  pdl_wait();
   for (int i = tid; i < 64; i += kStThreads) {
     s_bias[i] = p.bias != nullptr ? p.bias[i] : 0.f;
     s_sum[i] = affine ? p.bn_scale[i] : 0.f;
@@ -1955,7 +1958,6 @@ __global__ void __launch_bounds__(kStThreads, 2)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {

@@ -36,6 +36,14 @@ def main():
     train_loader, val_loader = cli.get_loader(cfg)
     tr = Trainer(train_data_loader=train_loader, val_data_loader=val_loader, config=cfg)
     tr.train_val()
+    # replicas must hold bit-identical weights after training (all-reduced gradients, identical Adam)
+    w_all = torch.cat([p_.detach().flatten() for p_ in tr.model.parameters()])
+    digest = torch.stack([w_all.double().sum(), w_all.double().abs().sum(), (w_all.double() * w_all.double()).sum()])
+    replicas_identical = True
+    if tr.world > 1:
+        gathered = [torch.zeros_like(digest) for _ in range(tr.world)]
+        dist.all_gather(gathered, digest)
+        replicas_identical = all(torch.equal(g_, gathered[0]) for g_ in gathered)
     acc = tr.test()                       # 44 images in batches of 3: the last batch holds 2 (ragged at world 2)
     # the same sweep with EVERY shard evaluated locally (same sub-batch shapes, hence the same kernel instantiations
     # and bit-identical predictions): integer counts, so the all-reduced result of the sharded run must be identical
@@ -85,6 +93,7 @@ def main():
                                                                         tr2_initial(ck)))
     if tr.rank == 0:
         res = {"world": tr.world, "test_acc": acc, "test_acc_ragged": acc, "test_acc_expected_ragged": expected,
+               "replicas_identical_after_training": replicas_identical,
                "checkpoint_keys": sorted(k for k in ck.keys()), "adam_step_at_save": adam_step,
                "resumed_epoch": tr2.start_epoch, "resumed_adam_step": resumed_step, "weights_restored": same_w,
                "loss_after_resume_finite": loss_ok, "module_prefix_checkpoint_loaded": prefixed_ok,

@@ -68,7 +68,7 @@ def test_main_py_synthetic_epoch_and_trainer_test(lib_built, tmp_path, world):
         _torchrun(world, args)
     res = json.load(open(tmp_path / "res.json"))
     print(res)
-    assert res["world"] == world
+    assert res["world"] == world and res["replicas_identical_after_training"]
     assert 0.0 <= res["test_acc"] <= 100.0 and res["test_acc_ragged"] == pytest.approx(res["test_acc_expected_ragged"], abs=1e-9)
     assert res["checkpoint_keys"] == ["epoch", "model_state", "optimizer_state", "scheduler_state"]
     assert res["resumed_epoch"] == 3  # the reference stores epoch + 1 AFTER incrementing it (trainer.py:74,258)

@@ -346,3 +346,38 @@ def test_wider_model_conv_dim_128_takes_the_unfused_head_paths(clk):
     pred, conf, ok = m2.evaluate_batch(x.cuda(), y.cuda(), nc=21, want_pred=True)
     with torch.no_grad():
         assert torch.equal(pred, m2(x.cuda()).argmax(1)) and int(conf.sum()) == y.numel()
+
+
+def test_first_inference_after_a_weight_update_reads_fresh_batchnorm_affine(clk):
+    """Regression: the direct stem kernel loaded the inference scale / shift (written by the bn_finalize launch right
+    before it) ABOVE its `griddepcontrol.wait`.  With a long kernel in front of bn_finalize (the weight re-pack of the
+    first forward after an optimiser step) the stem started early and used the previous forward's TRAINING-mode affine,
+    so the first evaluate_batch() after training differed from every later one.  Late-layer packing is forced onto the
+    main stream here so that the long kernel sits directly in front of bn_finalize -> stem, and a ~2 ms matmul is
+    queued first so that pack -> bn_finalize -> stem are all in the stream before any of them runs."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m = clk.UNet(21).to(dev)
+    opt = clk.FusedAdam(m.parameters(), lr=1e-3)
+    crit = clk.CrossEntropyDistillLoss(None)
+    m.engine.side_pack = False
+    blocker = torch.randn(8192, 8192, device=dev)
+    for it in range(6):
+        m.train()
+        x, y = structured_batch(300 + it, 2, 64, 64)
+        out = m(x.to(dev))
+        opt.zero_grad()
+        crit(out, y.to(dev)).backward()
+        opt.step()
+        m.eval()
+        x, y = structured_batch(400 + it, 1, 64, 64)
+        x, y = x.to(dev), y.to(dev)
+        counts = []
+        with torch.no_grad():
+            for _ in range(3):
+                c = torch.zeros(1, device=dev, dtype=torch.int64)
+                blocker @ blocker
+                _, conf, _ = m.evaluate_batch(x, y, nc=21, correct=c)
+                counts.append((int(c), conf.cpu()))
+        assert counts[0][0] == counts[1][0] == counts[2][0]
+        assert torch.equal(counts[0][1], counts[1][1]) and torch.equal(counts[1][1], counts[2][1])
