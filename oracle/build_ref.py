@@ -13,7 +13,6 @@ reference's own module on the box's host cores, and by tests/test_oracle_pinned.
 import marshal
 import os
 import py_compile
-import sys
 import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))

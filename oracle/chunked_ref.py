@@ -6,8 +6,6 @@ its OWN BatchNorm statistics (DataParallel replicas do not sync BN); the global-
 gradient the average of the per-chunk gradients; BN running stats follow chunk 0 (replica 0 shares
 its buffers with the master module).
 """
-import torch
-
 from .step_ref import forward_backward
 from .unet_ref import clone_sd
 
