@@ -78,6 +78,14 @@ def main():
         b = torch.zeros(64, device=dev)
         return lambda: ops.gemm_fprop(a, wf, b, 64, relu=True, stats=(ss, ss.clone()))
 
+    @case("stem_direct")
+    def _():
+        x = torch.randn(B, 3, S, S, device=dev)
+        wf = ops.pack_stem(torch.randn(64, 3, 3, 3, device=dev) * 0.2)
+        ss = torch.zeros(64, device=dev, dtype=torch.float64)
+        b = torch.zeros(64, device=dev)
+        return lambda: ops.stem_conv(x, wf, b, relu=True, stats=(ss, ss.clone()))
+
     @case("head")
     def _():
         a = t(B, S, S, 64)
